@@ -1,0 +1,120 @@
+"""Named synthetic cases (SURVEY §8 size table / BASELINE.json configs) and a
+builder that writes them in the reference's file formats."""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import synth
+
+CFG1_CTF = dict(CTF_DEFOCUS=(1.0, 4.0, 3), CTF_B_ENV=(2.0, 300.0, 1), CTF_AMPLITUDE=(0.1, 0.1, 1))
+DENSE_CTF = dict(CTF_DEFOCUS=(0.5, 4.5, 16), CTF_B_ENV=(2.0, 300.0, 8),
+                 CTF_AMPLITUDE=(0.05, 0.25, 2), SIGMA_PRIOR_B_CTF=50.0,
+                 SIGMA_PRIOR_DEFOCUS=0.4, PRIOR_DEFOCUS_CENTER=2.8)
+
+
+@dataclass
+class Case:
+    name: str
+    n_pixels: int
+    pixel_size: float
+    n_atoms: int
+    n_particles: int
+    quat_list: int            # which shipped list (576 / 4608 / 36864)
+    n_orient: int             # how many leading rows of it are used
+    ctf: dict = field(default_factory=dict)
+    max_disp: int = 10
+    grid_space: int = 1
+    write_angles: int = 0
+    model_sigma: float = 18.0
+    model_rmax: float = 45.0
+    particle_format: str = "text"   # "text" | "mrc"
+
+    @property
+    def n_ctf(self) -> int:
+        return int(self.ctf["CTF_AMPLITUDE"][2] * self.ctf["CTF_DEFOCUS"][2] * self.ctf["CTF_B_ENV"][2])
+
+    @property
+    def likelihoods(self) -> int:
+        return self.n_orient * self.n_ctf * self.n_particles
+
+
+CASES = {
+    # tiny known-answer cases (oracle / reference finish in well under a second)
+    "toy32": Case("toy32", 32, 1.5, 60, 3, 576, 24, CFG1_CTF, 4, 1, write_angles=3,
+                  model_sigma=5.0, model_rmax=12.0),
+    "toy36g2": Case("toy36g2", 36, 1.5, 60, 4, 576, 16, CFG1_CTF, 6, 2, model_sigma=6.0,
+                    model_rmax=14.0, particle_format="mrc"),
+    "toy64": Case("toy64", 64, 1.5, 200, 5, 576, 32, synth.PRODUCTION_GRID, 10, 1,
+                  model_sigma=10.0, model_rmax=26.0, particle_format="mrc"),
+    # BASELINE.json configs[0]: the reference's own CPU-runnable case
+    "cfg1": Case("cfg1", 128, 1.5, 1000, 10, 576, 576, CFG1_CTF, 10, 1),
+    # reduced 224-pixel case with the production grid (parity at the headline size)
+    "cfg2_slice": Case("cfg2_slice", 224, 1.0, 1000, 6, 4608, 8, synth.PRODUCTION_GRID, 40, 1,
+                       particle_format="mrc"),
+    # BASELINE.json configs[1]: the headline workload
+    "cfg2": Case("cfg2", 224, 1.0, 1000, 1000, 4608, 4608, synth.PRODUCTION_GRID, 40, 1,
+                 particle_format="mrc"),
+    "cfg3": Case("cfg3", 224, 1.0, 1000, 10000, 36864, 36864, synth.PRODUCTION_GRID, 40, 1,
+                 particle_format="mrc"),
+    "cfg4_slice": Case("cfg4_slice", 360, 2.0, 1000, 4, 4608, 4, DENSE_CTF, 40, 1,
+                       model_sigma=40.0, model_rmax=110.0, particle_format="mrc"),
+    "cfg5_slice": Case("cfg5_slice", 224, 1.0, 1000, 5, 4608, 12, synth.PRODUCTION_GRID, 40, 1,
+                       write_angles=10, particle_format="mrc"),
+}
+
+
+@dataclass
+class CaseData:
+    case: Case
+    model: np.ndarray        # [A,5] float64 (text-file precision)
+    quats: np.ndarray        # [O,4] float32
+    particles: np.ndarray    # [M,N,N] float32 as the reader will see them
+    truth: np.ndarray        # [M,4]
+    paths: dict
+
+
+def build_case(name_or_case, outdir: str | None = None, n_particles: int | None = None,
+               n_orient: int | None = None) -> CaseData:
+    c = CASES[name_or_case] if isinstance(name_or_case, str) else name_or_case
+    if n_particles is not None or n_orient is not None:
+        c = Case(**{**c.__dict__, "n_particles": n_particles or c.n_particles,
+                    "n_orient": n_orient or c.n_orient})
+    model = synth.make_model(c.n_atoms, seed=1, sigma=c.model_sigma, rmax=c.model_rmax)
+    quats = synth.load_quaternions(c.quat_list)[:c.n_orient].copy()
+    ctfp = synth.ctf_grid_params(c.ctf)
+    imgs, truth = synth.make_particles(model, quats, c.n_pixels, c.pixel_size, c.n_particles,
+                                       c.max_disp, ctfp, snr=0.1, seed=100,
+                                       normalise=(c.particle_format == "mrc"))
+    if c.particle_format == "text":
+        # the text format carries 8 decimals: make array == file
+        imgs = np.round(imgs.astype(np.float64), 8).astype(np.float32)
+    paths = {}
+    if outdir is not None:
+        os.makedirs(outdir, exist_ok=True)
+        paths = dict(model=os.path.join(outdir, "model.txt"), param=os.path.join(outdir, "param.txt"),
+                     orient=os.path.join(outdir, "orient.txt"),
+                     particles=os.path.join(outdir, "particles.mrc" if c.particle_format == "mrc"
+                                            else "particles.txt"))
+        synth.write_model_text(paths["model"], model)
+        synth.write_param_file(paths["param"], c.n_pixels, c.pixel_size, c.max_disp, c.grid_space,
+                               c.ctf, True, c.write_angles)
+        synth.write_orientation_list(paths["orient"], quats)
+        if c.particle_format == "mrc":
+            synth.write_particles_mrc(paths["particles"], imgs)
+        else:
+            synth.write_particles_text(paths["particles"], imgs)
+    return CaseData(c, model, quats, imgs, truth, paths)
+
+
+def reference_cli(cd: CaseData, outfile: str = "Output_Probabilities") -> list[str]:
+    """Command-line arguments (after the binary name) in the reference's CLI
+    (bioem.cpp:193-224) for a built case."""
+    a = ["--Modelfile", cd.paths["model"], "--Particlesfile", cd.paths["particles"],
+         "--Inputfile", cd.paths["param"], "--ReadOrientation", cd.paths["orient"],
+         "--OutputFile", outfile]
+    if cd.case.particle_format == "mrc":
+        a.append("--ReadMRC")
+    return a

@@ -1,0 +1,149 @@
+"""CPU-only: pins the restated oracle (oracle/bioem_oracle.cpp) against
+ (a) numpy for its FFT restatement,
+ (b) the committed outputs of the UNMODIFIED reference binary (tests/golden/*, made by
+     tools/make_golden.py from oracle/_ref/bioEM_ref),
+ (c) the reference's -DDEBUG_PROB per-evaluation stream (tests/golden/toy32/debug_prob.txt),
+ (d) a live run of oracle/_ref/bioEM_ref when that binary is present.
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from bioem_b200.cases import CASES, build_case, reference_cli
+from bioem_b200.outputs import parse_ang_prob, parse_debug_prob, parse_output_probabilities
+from oracle import pyoracle
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+REFBIN = os.path.join(ROOT, "oracle", "_ref", "bioEM_ref")
+
+# Q7 noise floor between two correct float implementations of the path: the reference is
+# built with -ffast-math, the oracle without; the log-posterior amplifies relative
+# rounding noise of the float sums by ~N^2/2.  Absolute tolerance on logP per image edge:
+LOGP_ATOL = {32: 5e-3, 36: 5e-3, 64: 2e-2, 128: 5e-2, 224: 0.3, 360: 1.0}
+
+
+@pytest.mark.parametrize("n", [8, 32, 36, 128, 224])
+def test_fft_matches_numpy(n):
+    L = pyoracle.lib()
+    rng = np.random.default_rng(n)
+    x = rng.normal(size=(n, n)).astype(np.float32)
+    X = np.zeros((n, n // 2 + 1, 2), dtype=np.float32)
+    for dbl in (0, 1):
+        pyoracle.set_fft_double(dbl)
+        L.oracle_fft_r2c(n, pyoracle._fp(x), pyoracle._fp(X))
+        ref = np.fft.rfft2(x.astype(np.float64))
+        got = X[..., 0] + 1j * X[..., 1]
+        scale = np.abs(ref).max()
+        assert np.abs(got - ref).max() < (3e-7 if dbl else 3e-6) * scale * np.log2(n)
+        y = np.zeros((n, n), dtype=np.float32)
+        Xc = X.copy()
+        L.oracle_fft_c2r(n, pyoracle._fp(Xc), pyoracle._fp(y))
+        assert np.abs(y / (n * n) - x).max() < 5e-6
+    pyoracle.set_fft_double(0)
+
+
+def _run_oracle(name):
+    cd = build_case(name)
+    P = pyoracle.Prepared(cd.case, cd.model, cd.quats, cd.particles)
+    return cd, P, P.run()
+
+
+def _check_against_reference_output(P, res, ref, n):
+    atol = LOGP_ATOL[n]
+    near_ties = 0
+    for m in range(P.M):
+        p = res["prob"][m]
+        logp = P.final_logprob(p["Total"], p["Constoadd"])
+        assert abs(logp - ref["logp"][m]) <= atol + 1e-4, (m, logp, ref["logp"][m])
+        assert abs(logp - ref["logp"][m]) <= 1e-4 * abs(ref["logp"][m])
+        assert abs(p["Constoadd"] - ref["const"][m]) <= atol + 1e-4
+        same = (p["cent_x"] == ref["cent_x"][m] and p["cent_y"] == ref["cent_y"][m]
+                and np.allclose(P.quats[p["orient"]], ref["angles"][m], atol=1.1e-4)
+                and abs(P.CtfParam[p["conv"], 0] - ref["amp"][m]) < 1.1e-4
+                and abs(P.CtfParam[p["conv"], 2] - ref["env"][m]) < 1.1e-4)
+        if not same:
+            # allowed only as a documented near-tie: the oracle's own runner-up is within
+            # the noise floor of its maximum
+            gap = p["Constoadd"] - res["second"][m]
+            assert gap <= atol, (m, gap, p, {k: v[m] for k, v in ref.items()})
+            near_ties += 1
+        else:
+            assert abs(p["norm"] - ref["norm"][m]) <= 1e-3 * abs(ref["norm"][m]) + 2e-4
+            assert abs(p["mu"] - ref["mu"][m]) <= 1e-3 * abs(ref["mu"][m]) + 2e-4
+    return near_ties
+
+
+@pytest.mark.parametrize("name", ["toy32", "toy36g2", "toy64", "cfg1", "cfg2_slice", "cfg5_slice"])
+def test_oracle_matches_reference_golden(name, golden_dir):
+    cd, P, res = _run_oracle(name)
+    ref = parse_output_probabilities(os.path.join(golden_dir, name, "Output_Probabilities"))
+    assert len(ref["logp"]) == P.M
+    _check_against_reference_output(P, res, ref, cd.case.n_pixels)
+
+
+@pytest.mark.parametrize("name", ["toy32", "cfg5_slice"])
+def test_oracle_angle_table_matches_reference(name, golden_dir):
+    cd, P, res = _run_oracle(name)
+    ang = parse_ang_prob(os.path.join(golden_dir, name, "ANG_PROB"))
+    K = cd.case.write_angles
+    atol = LOGP_ATOL[cd.case.n_pixels]
+    for m in range(P.M):
+        pa = res["angle"][:, m]
+        logp = np.array([P.final_logprob(t, c) for t, c in zip(pa["forAngles"], pa["ConstAngle"])])
+        order = np.argsort(-logp, kind="stable")[:K]
+        assert len(ang[m]) == K
+        for k in range(K):
+            assert abs(ang[m][k]["logp"] - logp[order[k]]) <= atol + 1e-4
+            if not np.allclose(P.quats[order[k]], ang[m][k]["angles"], atol=1.1e-4):
+                # order swap only between orientations closer than the noise floor
+                j = [i for i in range(P.O) if np.allclose(P.quats[i], ang[m][k]["angles"], atol=1.1e-4)]
+                assert j and abs(logp[j[0]] - logp[order[k]]) <= atol
+
+
+def test_oracle_matches_reference_debug_stream(golden_dir):
+    """Per-evaluation ground truth: value and float-narrowed logpro of every displacement,
+    in the reference's enumeration order (bioem_algorithm.h:156-197)."""
+    txt = open(os.path.join(golden_dir, "toy32", "debug_prob.txt")).read()
+    rows = parse_debug_prob(txt)
+    cd = build_case("toy32")
+    P = pyoracle.Prepared(cd.case, cd.model, cd.quats, cd.particles)
+    res = P.run(0, 2, trace_image=0)
+    assert rows.shape[0] == 2 * 2 * P.D
+    k = 0
+    maxd, G, N = cd.case.max_disp, cd.case.grid_space, cd.case.n_pixels
+    xs = list(range(0, maxd + 1, G)) + [c - N for c in range(N - maxd, N, G)]
+    for o in range(2):
+        for c in range(2):
+            d = 0
+            for dx in xs:
+                for dy in xs:
+                    r = rows[k]
+                    assert (int(r[0]), int(r[1]), int(r[2]), int(r[3]), int(r[4])) == (0, o, c, dx, dy)
+                    v = res["trace_value"][o, c, d]
+                    lp = res["trace_logpro"][o, c, d]
+                    assert abs(v - r[5]) <= 2e-6 * max(1.0, abs(r[5])) + 1e-6
+                    assert abs(lp - r[6]) <= 2e-3
+                    k += 1
+                    d += 1
+
+
+@pytest.mark.skipif(not os.path.exists(REFBIN), reason="reference binary not built (oracle/_ref)")
+def test_reference_binary_live_matches_golden(tmp_path, golden_dir):
+    cd = build_case("toy64", str(tmp_path))
+    r = subprocess.run([REFBIN] + reference_cli(cd), cwd=str(tmp_path), capture_output=True,
+                       text=True, env={**os.environ, "OMP_NUM_THREADS": "2"})
+    assert r.returncode == 0, r.stdout[-1000:]
+    a = parse_output_probabilities(os.path.join(tmp_path, "Output_Probabilities"))
+    b = parse_output_probabilities(os.path.join(golden_dir, "toy64", "Output_Probabilities"))
+    np.testing.assert_allclose(a["logp"], b["logp"], atol=1e-3)
+    assert (a["cent_x"] == b["cent_x"]).all() and (a["cent_y"] == b["cent_y"]).all()
+
+
+def test_displacement_count_quirk_q3():
+    L = pyoracle.lib()
+    assert L.oracle_num_displacements(224, 40, 1) == 81 * 81
+    assert L.oracle_num_displacements(36, 6, 2) == 7 * 7
+    # maxD % G != 0: Algo 1 enumerates floor(maxD/G)+1+ceil(maxD/G) per axis
+    assert L.oracle_num_displacements(64, 5, 2) == (3 + 3) ** 2
