@@ -1,0 +1,1008 @@
+// sm_100a kernels for the BioEM likelihood path.
+//
+//   stage 1  project_kernel        createProjection        (reference bioem.cpp:1604-1818)
+//            fft_rows_kernel /     forward r2c 2-D FFT     (reference bioem.cpp:1848)
+//            fft_cols_kernel
+//   stage 2  ctf_conv_kernel       createConvolutedProjectionMap (bioem.cpp:1855-1923)
+//   stage 3-5 likelihood_kernel    calculateCCFFT + doRefMapFFT + calProb, fused
+//                                  (bioem.cpp:1435-1459, bioem_algorithm.h:18-198)
+//            merge_partials_kernel / finalize_kernel
+//
+// Data layout in HBM ("packed half-spectrum"): a real N x N image has the
+// half-spectrum A[kx][ky], kx < N, ky <= N/2.  With N = R1*R2 (bfft::Geo<N>),
+// NCOL = N/2 and KC columns per chunk, element (kx = n1*R2 + n2, ky = ch*KC + kyl)
+// with ky < NCOL lives in float4 number
+//      ((ch*(R1/2) + n1/2)*R2 + n2)*KC + kyl ,   .xy if n1 even, .zw if n1 odd,
+// i.e. exactly the order in which the column pass of the fused kernel reads it
+// (one fully coalesced LDG.128 per thread per two points).  The Nyquist column
+// ky = N/2 is a tail of N/2 float4: tail[(n1/2)*R2 + n2].
+#pragma once
+#include "fft_regs.cuh"
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace bioem
+{
+
+constexpr int NT = 256; // threads per CTA for the FFT kernels
+
+template <int N> struct Lay
+{
+  using G = bfft::Geo<N>;
+  static constexpr int R1 = G::R1, R2 = G::R2, KC = G::KC, PC = G::PC;
+  static constexpr int NCOL = N / 2;
+  static constexpr int NCH = NCOL / KC;
+  static constexpr int MAIN4 = NCOL * N / 2;
+  static constexpr int TAIL4 = N / 2;
+  static constexpr int MAP4 = MAIN4 + TAIL4;
+  static_assert(PC * R2 <= NT && PC * R1 <= NT, "row-pass chunk must fit one item per thread");
+  __host__ __device__ static constexpr int main_idx(int ch, int n1p, int n2, int kyl)
+  {
+    return ((ch * (R1 / 2) + n1p) * R2 + n2) * KC + kyl;
+  }
+};
+
+struct ConvParam
+{
+  float sumC;
+  float sumsqC;
+  double Bterm; // (Nt/2-2)*log((Nt-2)*ForLogProb) - prior(c)   (bioem_algorithm.h:42-67)
+};
+
+// best-so-far record of one image (bioem_Probability_map + what is needed to
+// finish norm/mu later)
+struct Running
+{
+  double Const;
+  double Total;
+  float lpf; // float-narrowed logpro of the current maximum
+  int orient;
+  int conv;
+  int lin; // displacement enumeration index wx*nw + wy
+  float v; // correlation value at the maximum
+  float sumC;
+  float sumsqC;
+  int pad;
+};
+
+struct ProbMapOut // == bioem_Probability_map, include/map.h:116-129 (40 bytes)
+{
+  double Total;
+  double Constoadd;
+  int max_prob_cent_x, max_prob_cent_y, max_prob_orient, max_prob_conv;
+  float max_prob_norm, max_prob_mu;
+};
+struct ProbAngleOut // == bioem_Probability_angle, include/map.h:131-135
+{
+  double forAngles;
+  double ConstAngle;
+};
+
+constexpr double kMinProb = -999999.; // defs.h:65
+
+__device__ __forceinline__ float4 ldg4(const float4 *p) { return __ldg(p); }
+
+// ===========================================================================
+// layout conversion: standard [N][N/2+1] interleaved complex <-> packed
+// ===========================================================================
+template <int N>
+__global__ void pack_kernel(const float2 *__restrict__ std_maps, float4 *__restrict__ packed, int nmaps)
+{
+  using L = Lay<N>;
+  const int map = blockIdx.y;
+  if (map >= nmaps)
+    return;
+  const float2 *src = std_maps + (size_t) map * N * (N / 2 + 1);
+  float4 *dst = packed + (size_t) map * L::MAP4;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L::MAP4; i += gridDim.x * blockDim.x)
+  {
+    int n1p, n2, ky;
+    if (i < L::MAIN4)
+    {
+      int kyl = i % L::KC;
+      int t = i / L::KC;
+      n2 = t % L::R2;
+      t /= L::R2;
+      n1p = t % (L::R1 / 2);
+      int ch = t / (L::R1 / 2);
+      ky = ch * L::KC + kyl;
+    }
+    else
+    {
+      int t = i - L::MAIN4;
+      n2 = t % L::R2;
+      n1p = t / L::R2;
+      ky = L::NCOL;
+    }
+    const int kx0 = (2 * n1p) * L::R2 + n2, kx1 = (2 * n1p + 1) * L::R2 + n2;
+    float2 a = src[(size_t) kx0 * (N / 2 + 1) + ky], b = src[(size_t) kx1 * (N / 2 + 1) + ky];
+    dst[i] = make_float4(a.x, a.y, b.x, b.y);
+  }
+}
+
+template <int N>
+__global__ void unpack_kernel(const float4 *__restrict__ packed, float2 *__restrict__ std_maps, int nmaps)
+{
+  using L = Lay<N>;
+  const int map = blockIdx.y;
+  if (map >= nmaps)
+    return;
+  float2 *dst = std_maps + (size_t) map * N * (N / 2 + 1);
+  const float4 *src = packed + (size_t) map * L::MAP4;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L::MAP4; i += gridDim.x * blockDim.x)
+  {
+    int n1p, n2, ky;
+    if (i < L::MAIN4)
+    {
+      int kyl = i % L::KC;
+      int t = i / L::KC;
+      n2 = t % L::R2;
+      t /= L::R2;
+      n1p = t % (L::R1 / 2);
+      int ch = t / (L::R1 / 2);
+      ky = ch * L::KC + kyl;
+    }
+    else
+    {
+      int t = i - L::MAIN4;
+      n2 = t % L::R2;
+      n1p = t / L::R2;
+      ky = L::NCOL;
+    }
+    const int kx0 = (2 * n1p) * L::R2 + n2, kx1 = (2 * n1p + 1) * L::R2 + n2;
+    float4 v = src[i];
+    dst[(size_t) kx0 * (N / 2 + 1) + ky] = make_float2(v.x, v.y);
+    dst[(size_t) kx1 * (N / 2 + 1) + ky] = make_float2(v.z, v.w);
+  }
+}
+
+// ===========================================================================
+// stage 1a: projection (rotate, rasterise).  One CTA per (orientation, band of
+// image rows); the band lives in shared memory; inside the CTA every warp owns a
+// contiguous sub-band and walks ALL model points in order, so each pixel receives
+// its contributions in model-point order exactly like the reference's sequential
+// loop (deterministic, no atomics).  FP32 operations are written with explicit
+// round-to-nearest intrinsics in the reference's evaluation order so that the
+// pixel a point lands on and the weight it adds are those of the CPU code.
+// ===========================================================================
+struct ProjParams
+{
+  const float4 *xyzr; // model points: x, y, z, radius
+  const float *dens;  // density
+  const float4 *angles;
+  float *proj;      // [OB][N*N]
+  double *tempden;  // [OB][nbands]
+  int *skipped;     // [OB] (points out of frame), optional
+  int A;
+  int N;
+  int band_rows;
+  int nbands;
+  int o_base; // first orientation of the batch (index into angles)
+  int doquater;
+  int shiftX, shiftY;
+  float pixelSize;
+};
+
+__global__ void __launch_bounds__(256) project_kernel(ProjParams p)
+{
+  extern __shared__ float band[]; // band_rows * N
+  const int N = p.N;
+  const int ob = blockIdx.x, b = blockIdx.y;
+  const int r0 = b * p.band_rows;
+  const int r1 = min(N, r0 + p.band_rows);
+  const int rows = r1 - r0;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  for (int i = tid; i < rows * N; i += blockDim.x)
+    band[i] = 0.f;
+
+  // rotation matrix, reference evaluation order (bioem.cpp:1638-1672)
+  const float4 q = p.angles[p.o_base + ob];
+  float m00, m01, m02, m10, m11, m12;
+  if (p.doquater)
+  {
+    const float q0 = q.x, q1 = q.y, q2 = q.z, q3 = q.w;
+    m00 = __fsub_rn(__fsub_rn(1.f, __fmul_rn(__fmul_rn(2.f, q1), q1)), __fmul_rn(__fmul_rn(2.f, q2), q2));
+    m10 = __fmul_rn(2.f, __fsub_rn(__fmul_rn(q0, q1), __fmul_rn(q2, q3)));
+    m01 = __fmul_rn(2.f, __fadd_rn(__fmul_rn(q0, q1), __fmul_rn(q2, q3)));
+    m11 = __fsub_rn(__fsub_rn(1.f, __fmul_rn(__fmul_rn(2.f, q0), q0)), __fmul_rn(__fmul_rn(2.f, q2), q2));
+    m02 = __fmul_rn(2.f, __fsub_rn(__fmul_rn(q0, q2), __fmul_rn(q1, q3)));
+    m12 = __fmul_rn(2.f, __fadd_rn(__fmul_rn(q1, q2), __fmul_rn(q0, q3)));
+  }
+  else
+  {
+    const float al = q.x, be = q.y, ga = q.z;
+    const float ca = cosf(al), sa = sinf(al), cb = cosf(be), sb = sinf(be), cg = cosf(ga), sg = sinf(ga);
+    m00 = __fsub_rn(__fmul_rn(cg, ca), __fmul_rn(__fmul_rn(cb, sa), sg));
+    m01 = __fadd_rn(__fmul_rn(cg, sa), __fmul_rn(__fmul_rn(cb, ca), sg));
+    m02 = __fmul_rn(sg, sb);
+    m10 = __fsub_rn(__fmul_rn(-sg, ca), __fmul_rn(__fmul_rn(cb, sa), cg));
+    m11 = __fadd_rn(__fmul_rn(-sg, sa), __fmul_rn(__fmul_rn(cb, ca), cg));
+    m12 = __fmul_rn(cg, sb);
+  }
+  __syncthreads();
+
+  // this warp's rows
+  const int h = (rows + nwarps - 1) / nwarps;
+  const int wr0 = r0 + warp * h;
+  const int wr1 = min(r1, wr0 + h);
+  const float px = p.pixelSize;
+  const float half = __fdiv_rn((float) N, 2.0f);
+  float td = 0.f; // per-lane share of tempden
+  int nskip = 0;
+  for (int n = 0; n < p.A; n++)
+  {
+    const float4 pt = __ldg(&p.xyzr[n]);
+    const float den = __ldg(&p.dens[n]);
+    const float rx = __fadd_rn(__fadd_rn(__fadd_rn(0.f, __fmul_rn(m00, pt.x)), __fmul_rn(m01, pt.y)), __fmul_rn(m02, pt.z));
+    const float ry = __fadd_rn(__fadd_rn(__fadd_rn(0.f, __fmul_rn(m10, pt.x)), __fmul_rn(m11, pt.y)), __fmul_rn(m12, pt.z));
+    int i = (int) floorf(__fadd_rn(__fadd_rn(__fdiv_rn(rx, px), half), 0.5f));
+    int j = (int) floorf(__fadd_rn(__fadd_rn(__fdiv_rn(ry, px), half), 0.5f));
+    const float radius = pt.w;
+    if (radius <= px)
+    {
+      if (i < 0 || j < 0 || i >= N || j >= N)
+      {
+        nskip++;
+        continue;
+      }
+      if (i >= wr0 && i < wr1 && lane == 0)
+      {
+        band[(i - r0) * N + j] = __fadd_rn(band[(i - r0) * N + j], den);
+        td = __fadd_rn(td, den);
+      }
+    }
+    else
+    {
+      i -= p.shiftX;
+      j -= p.shiftY;
+      const int irad = (int) __fdiv_rn(radius, px) + 1;
+      if (i < irad || j < irad || i >= N - irad || j >= N - irad)
+      {
+        nskip++;
+        continue;
+      }
+      if (i + irad < wr0 || i - irad >= wr1)
+        continue;
+      const float rad2 = __fmul_rn(radius, radius);
+      const int S = 2 * irad + 1;
+      const double denom = 4 * 3.14159265358979323846 * (double) radius * (double) rad2;
+      for (int idx = lane; idx < S * S; idx += 32)
+      {
+        const int di = idx / S - irad, dj = idx % S - irad;
+        const int ii = i + di, jj = j + dj;
+        if (ii < wr0 || ii >= wr1)
+          continue;
+        // dist = ((float)(di)*di + dj*dj) * px * px
+        const float dist = __fmul_rn(__fmul_rn(__fadd_rn(__fmul_rn((float) di, (float) di), (float) (dj * dj)), px), px);
+        if (dist < rad2)
+        {
+          const float num = __fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(px, px), 2.f), sqrtf(__fsub_rn(rad2, dist))), den), 3.f);
+          const double w = (double) num / denom;
+          float *px_ = &band[(ii - r0) * N + jj];
+          *px_ = (float) ((double) *px_ + w);
+          td = (float) ((double) td + w);
+        }
+      }
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  float *out = p.proj + (size_t) ob * N * N + (size_t) r0 * N;
+  for (int i = tid; i < rows * N; i += blockDim.x)
+    out[i] = band[i];
+  // deterministic reduction of the tempden shares: lanes then warps, fixed order
+  __shared__ float s_td[256];
+  s_td[tid] = td;
+  __syncthreads();
+  if (tid == 0)
+  {
+    double t = 0.0;
+    for (int k = 0; k < (int) blockDim.x; k++)
+      t += (double) s_td[k];
+    p.tempden[(size_t) ob * p.nbands + b] = t;
+    if (p.skipped && b == 0)
+      p.skipped[ob] = nskip;
+  }
+}
+
+// ===========================================================================
+// stage 1b: forward 2-D r2c FFT of real images -> packed half-spectrum.
+// rows pass (two real rows per complex transform) to a row-major scratch
+// [img][N][N/2+1], then column pass into the packed layout.
+// scale[img] (optional): multiply the image by NormDen / sum_b tempden[img][b]
+// (bioem.cpp:1808-1818) while loading.
+// ===========================================================================
+template <int N>
+__global__ void __launch_bounds__(NT) fft_rows_kernel(const float *__restrict__ imgs, const double *__restrict__ tempden,
+                                                      int nbands, float normDen, const float2 *__restrict__ tw_fwd,
+                                                      float2 *__restrict__ scratch)
+{
+  using L = Lay<N>;
+  constexpr int R1 = L::R1, R2 = L::R2, PC = L::PC;
+  constexpr int NPAIR = N / 2;
+  __shared__ float2 E[PC * N];
+  __shared__ float2 TW[N];
+  const int tid = threadIdx.x;
+  const int img = blockIdx.y;
+  const int p0 = blockIdx.x * PC;
+  const int npl = min(PC, NPAIR - p0);
+  for (int i = tid; i < N; i += NT)
+    TW[i] = tw_fwd[i];
+  float scale = 1.f;
+  if (tempden)
+  {
+    double t = 0.0;
+    for (int b = 0; b < nbands; b++)
+      t += tempden[(size_t) img * nbands + b];
+    scale = __fdiv_rn(normDen, (float) t);
+  }
+  const float *src = imgs + (size_t) img * N * N;
+  __syncthreads();
+  // pass 1
+  {
+    const int pl = tid / R2, n2 = tid % R2;
+    if (pl < npl)
+    {
+      const float *ra = src + (size_t) (2 * (p0 + pl)) * N;
+      const float *rb = ra + N;
+      float2 x[R1];
+#pragma unroll
+      for (int n1 = 0; n1 < R1; n1++)
+        x[n1] = make_float2(__fmul_rn(ra[n1 * R2 + n2], scale), __fmul_rn(rb[n1 * R2 + n2], scale));
+      bfft::Dft<R1, -1>::run(x);
+#pragma unroll
+      for (int k1 = 1; k1 < R1; k1++)
+        x[k1] = bfft::cmul(x[k1], TW[n2 * R1 + k1]);
+#pragma unroll
+      for (int k1 = 0; k1 < R1; k1++)
+        E[pl * N + k1 * R2 + ((n2 + k1) % R2)] = x[k1];
+    }
+  }
+  __syncthreads();
+  // pass 2 (results kept in registers across the barrier, then written back in natural order)
+  for (int base = 0; base < npl * R1; base += NT)
+  {
+    const int item = base + tid;
+    const bool act = item < npl * R1;
+    const int pl = act ? item / R1 : 0, k1 = act ? item % R1 : 0;
+    float2 y[R2];
+    if (act)
+    {
+#pragma unroll
+      for (int n2 = 0; n2 < R2; n2++)
+        y[n2] = E[pl * N + k1 * R2 + ((n2 + k1) % R2)];
+      bfft::Dft<R2, -1>::run(y);
+    }
+    __syncthreads();
+    if (act)
+    {
+#pragma unroll
+      for (int k2 = 0; k2 < R2; k2++)
+        E[pl * N + k1 + R1 * k2] = y[k2];
+    }
+    // (npl*R1 <= NT always holds for the shipped geometries, so one trip)
+  }
+  __syncthreads();
+  // separate the two real rows: A = (Z[k] + conj Z[N-k])/2, B = (Z[k] - conj Z[N-k])/(2i)
+  float2 *dst = scratch + (size_t) img * N * (N / 2 + 1);
+  for (int i = tid; i < npl * (N / 2 + 1); i += NT)
+  {
+    const int pl = i / (N / 2 + 1), k = i % (N / 2 + 1);
+    const float2 z = E[pl * N + k], zc = E[pl * N + ((N - k) % N)];
+    const float2 a = make_float2(0.5f * (z.x + zc.x), 0.5f * (z.y - zc.y));
+    const float2 bb = make_float2(0.5f * (z.y + zc.y), -0.5f * (z.x - zc.x));
+    dst[(size_t) (2 * (p0 + pl)) * (N / 2 + 1) + k] = a;
+    dst[(size_t) (2 * (p0 + pl) + 1) * (N / 2 + 1) + k] = bb;
+  }
+}
+
+template <int N>
+__global__ void __launch_bounds__(NT) fft_cols_kernel(const float2 *__restrict__ scratch, const float2 *__restrict__ tw_fwd,
+                                                      float4 *__restrict__ packed)
+{
+  using L = Lay<N>;
+  constexpr int R1 = L::R1, R2 = L::R2, KC = L::KC;
+  constexpr int NC1 = N / 2 + 1;
+  extern __shared__ __align__(16) unsigned char smem_cols[];
+  float2 *E = reinterpret_cast<float2 *>(smem_cols); // [KC * N]
+  float2 *TW = E + KC * N;                           // [N]
+  const int tid = threadIdx.x;
+  const int img = blockIdx.y;
+  const int ch = blockIdx.x; // NCH chunks + one extra for the Nyquist column
+  const int ky0 = ch * KC;
+  const int ncol = min(KC, NC1 - ky0);
+  for (int i = tid; i < N; i += NT)
+    TW[i] = tw_fwd[i];
+  const float2 *src = scratch + (size_t) img * N * NC1;
+  float2 *dst2 = reinterpret_cast<float2 *>(packed + (size_t) img * L::MAP4);
+  __syncthreads();
+  for (int item = tid; item < R2 * KC; item += NT)
+  {
+    const int n2 = item / KC, kyl = item % KC;
+    if (kyl < ncol)
+    {
+      float2 x[R1];
+#pragma unroll
+      for (int n1 = 0; n1 < R1; n1++)
+        x[n1] = src[(size_t) (n1 * R2 + n2) * NC1 + ky0 + kyl];
+      bfft::Dft<R1, -1>::run(x);
+#pragma unroll
+      for (int k1 = 1; k1 < R1; k1++)
+        x[k1] = bfft::cmul(x[k1], TW[n2 * R1 + k1]);
+#pragma unroll
+      for (int k1 = 0; k1 < R1; k1++)
+        E[(k1 * R2 + n2) * KC + kyl] = x[k1];
+    }
+  }
+  __syncthreads();
+  for (int item = tid; item < R1 * KC; item += NT)
+  {
+    const int k1 = item / KC, kyl = item % KC;
+    if (kyl < ncol)
+    {
+      float2 y[R2];
+#pragma unroll
+      for (int n2 = 0; n2 < R2; n2++)
+        y[n2] = E[(k1 * R2 + n2) * KC + kyl];
+      bfft::Dft<R2, -1>::run(y);
+#pragma unroll
+      for (int k2 = 0; k2 < R2; k2++)
+      {
+        const int kx = k1 + R1 * k2;
+        const int n1 = kx / R2, m2 = kx % R2;
+        size_t f4;
+        if (ch < L::NCH)
+          f4 = (size_t) L::main_idx(ch, n1 / 2, m2, kyl);
+        else
+          f4 = (size_t) L::MAIN4 + (n1 / 2) * R2 + m2;
+        dst2[f4 * 2 + (n1 & 1)] = y[k2];
+      }
+    }
+  }
+}
+
+// per-image sum and sum of squares, strictly sequential float accumulation in
+// row-major order like the reference (bioem.cpp:2087-2107); one-off input prep.
+__global__ void image_sums_kernel(const float *__restrict__ imgs, int n2, int M, float *__restrict__ sum,
+                                  float *__restrict__ sumsq)
+{
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M)
+    return;
+  const float *p = imgs + (size_t) m * n2;
+  float s = 0.f, ss = 0.f;
+  for (int i = 0; i < n2; i++)
+  {
+    const float v = p[i];
+    s = __fadd_rn(s, v);
+    ss = __fadd_rn(ss, __fmul_rn(v, v));
+  }
+  sum[m] = s;
+  sumsq[m] = ss;
+}
+
+// ===========================================================================
+// stage 2: V = P * conj(K_c) on packed maps, sumC, sumsquareC, and the
+// displacement-independent part of the log-posterior.
+// ===========================================================================
+template <int N>
+__global__ void __launch_bounds__(NT) ctf_conv_kernel(const float4 *__restrict__ proj, const float4 *__restrict__ ctf,
+                                                      const double *__restrict__ prior, float4 *__restrict__ conv,
+                                                      ConvParam *__restrict__ cpar, int C, float Ntotpi)
+{
+  using L = Lay<N>;
+  const int c = blockIdx.x, ob = blockIdx.y, tid = threadIdx.x;
+  const float4 *P = proj + (size_t) ob * L::MAP4;
+  const float4 *K = ctf + (size_t) c * L::MAP4;
+  float4 *V = conv + ((size_t) ob * C + c) * L::MAP4;
+  float acc = 0.f;
+  float sumC = 0.f;
+  for (int i = tid; i < L::MAP4; i += NT)
+  {
+    const float4 a = P[i], k = K[i];
+    float4 v;
+    v.x = a.x * k.x + a.y * k.y;
+    v.y = a.y * k.x - a.x * k.y;
+    v.z = a.z * k.z + a.w * k.w;
+    v.w = a.w * k.z - a.z * k.w;
+    V[i] = v;
+    // Hermitian weights (bioem.cpp:1893-1914): 1 for ky = 0 and ky = N/2, else 2
+    float w = 2.f;
+    if (i >= L::MAIN4)
+      w = 1.f;
+    else if ((i % L::KC) == 0 && (i / (L::KC * L::R2 * (L::R1 / 2))) == 0)
+      w = 1.f;
+    acc += w * (v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w);
+    if (i == 0)
+      sumC = v.x; // kx = 0, ky = 0
+  }
+  __shared__ float red[NT];
+  red[tid] = acc;
+  __syncthreads();
+  for (int s = NT / 2; s > 0; s >>= 1)
+  {
+    if (tid < s)
+      red[tid] += red[tid + s];
+    __syncthreads();
+  }
+  if (tid == 0)
+  {
+    const float ssC = __fdiv_rn(red[0], (float) (N * N));
+    ConvParam cp;
+    cp.sumC = sumC;
+    cp.sumsqC = ssC;
+    const float fl = __fsub_rn(__fmul_rn(ssC, Ntotpi), __fmul_rn(sumC, sumC));
+    cp.Bterm = ((double) Ntotpi * 0.5 - 2.0) * log((double) __fsub_rn(Ntotpi, 2.f) * (double) fl) - prior[c];
+    cpar[(size_t) ob * C + c] = cp;
+  }
+}
+
+// ===========================================================================
+// stages 3-5 fused.  One CTA owns one particle image m and a group of
+// orientations of the current batch; for every (orientation, CTF) pair it
+//   * streams the conv spectrum (L2) and the particle spectrum (L2/HBM) with
+//     coalesced 128-bit loads, multiplies conv * conj(particle) in registers,
+//   * runs the column pass of the inverse 2-D FFT keeping only the displacement
+//     window rows (output pruning) in shared memory,
+//   * runs the row pass two real rows at a time, in place,
+//   * evaluates the analytic log-posterior's displacement-dependent factor
+//     (firstele, FP32, reference operation order) straight out of the FFT
+//     registers, and reduces (min firstele <=> max logpro, sum of exp) in the CTA,
+//   * folds the result into the image's running (Constoadd, Total, arg-max)
+//     kept in registers of the bookkeeping thread.
+// No correlation map ever leaves the SM.
+// ===========================================================================
+struct LikParams
+{
+  const float4 *convs; // [OBcur*C][MAP4]
+  const float4 *refs;  // [M][MAP4]
+  const ConvParam *cpar;
+  const float *sumRef;
+  const float *sumsqRef;
+  const float2 *tw_inv;      // [N]  exp(+2 pi i n2*k1/N) at [n2*R1 + k1]
+  const unsigned char *wtab; // [N]  window index of a raw displacement, 255 = outside
+  Running *partials;         // [NG][M]
+  ProbAngleOut *angles;      // [O][M] or null
+  float *dbg_values;         // optional [OBcur*C][M][nw*nw] correlation values
+  int M, C, OBcur, OG, o_base;
+  int nw;  // window points per axis
+  int nwp; // nw rounded up to even
+  float Ntotpi;
+  float invNN;
+  float acoef_f; // (3 - Nt)/2
+  double acoef_d;
+  float tcut; // relative firstele excess beyond which exp() underflows to nothing
+};
+
+template <int N> __host__ __device__ constexpr size_t lik_smem_bytes(int nw)
+{
+  using L = Lay<N>;
+  const int nwp = nw + (nw & 1);
+  size_t e_words = (size_t) L::KC * N * 2; // floats
+  size_t fe_words = (size_t) nw * nw;
+  size_t ex = e_words > fe_words ? e_words : fe_words;
+  ex = (ex + 3) & ~(size_t) 3;
+  return ((size_t) nwp * L::NCOL * 2 + ex + (size_t) N * 2) * sizeof(float) + ((N + 15) & ~15);
+}
+
+__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int m)
+{
+  unsigned lo = (unsigned) v, hi = (unsigned) (v >> 32);
+  lo = __shfl_xor_sync(0xffffffffu, lo, m);
+  hi = __shfl_xor_sync(0xffffffffu, hi, m);
+  return ((unsigned long long) hi << 32) | lo;
+}
+
+template <int N> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)) likelihood_kernel(LikParams p)
+{
+  using L = Lay<N>;
+  constexpr int R1 = L::R1, R2 = L::R2, KC = L::KC, PC = L::PC, NCOL = L::NCOL, NCH = L::NCH;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int nw = p.nw, nwp = p.nwp;
+  float2 *Y = reinterpret_cast<float2 *>(smem_raw); // [nwp][NCOL]
+  float2 *E = Y + (size_t) nwp * NCOL;             // [KC*N], aliased by FE
+  float *FE = reinterpret_cast<float *>(E);
+  size_t ex = (size_t) KC * N * 2 > (size_t) nw * nw ? (size_t) KC * N * 2 : (size_t) nw * nw;
+  ex = (ex + 3) & ~(size_t) 3;
+  float2 *TW = reinterpret_cast<float2 *>(FE + ex);
+  unsigned char *WT = reinterpret_cast<unsigned char *>(TW + N);
+  __shared__ unsigned long long s_key[2];
+  __shared__ float s_wsum[2][NT / 32];
+  __shared__ float s_winv[2];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int m = blockIdx.x % p.M;
+  const int g = blockIdx.x / p.M;
+  const int o_lo = g * p.OG;
+  const int o_hi = min(p.OBcur, o_lo + p.OG);
+
+  for (int i = tid; i < N; i += NT)
+  {
+    TW[i] = p.tw_inv[i];
+    WT[i] = p.wtab[i];
+  }
+  if (tid < 2)
+    s_key[tid] = ~0ull;
+
+  const float4 *ref = p.refs + (size_t) m * L::MAP4;
+  const float sR = p.sumRef[m], ssR = p.sumsqRef[m];
+  const float Nt = p.Ntotpi;
+
+  // bookkeeping state (meaningful in thread 0 only)
+  double bk_Const = kMinProb, bk_Total = 0.0;
+  float bk_lpf = 0.f, bk_v = 0.f, bk_sC = 0.f, bk_ssC = 0.f;
+  int bk_o = 0, bk_c = 0, bk_lin = 0;
+  double an_Const = kMinProb, an_Total = 0.0;
+
+  int buf = 0;
+  __syncthreads();
+
+  for (int ol = o_lo; ol < o_hi; ol++)
+  {
+    an_Const = kMinProb;
+    an_Total = 0.0;
+    for (int c = 0; c < p.C; c++)
+    {
+      const int oc = ol * p.C + c;
+      const float4 *conv = p.convs + (size_t) oc * L::MAP4;
+      const ConvParam cp = p.cpar[oc];
+      // firstele = Nt*(ssR*ssC - v*v) + 2*sR*sC*v - ssR*sC*sC - sR*sR*ssC   (FP32, source order)
+      const float f_a = __fmul_rn(ssR, cp.sumsqC);
+      const float f_b = __fmul_rn(__fmul_rn(2.f, sR), cp.sumC);
+      const float f_c = __fmul_rn(__fmul_rn(ssR, cp.sumC), cp.sumC);
+      const float f_d = __fmul_rn(__fmul_rn(sR, sR), cp.sumsqC);
+
+      if (nw & 1) // zero the padding row of the last row pair
+        for (int i = tid; i < NCOL; i += NT)
+          Y[(size_t) nw * NCOL + i] = make_float2(0.f, 0.f);
+
+      // ------------------------------------------------ column pass (along kx)
+      for (int ch = 0; ch < NCH; ch++)
+      {
+        for (int item = tid; item < R2 * KC; item += NT)
+        {
+          const int n2 = item / KC, kyl = item % KC;
+          float2 x[R1];
+          const int base = L::main_idx(ch, 0, n2, kyl);
+#pragma unroll
+          for (int n1p = 0; n1p < R1 / 2; n1p++)
+          {
+            const float4 r = ldg4(ref + base + n1p * R2 * KC);
+            const float4 v = ldg4(conv + base + n1p * R2 * KC);
+            x[2 * n1p] = bfft::cmulc(make_float2(v.x, v.y), make_float2(r.x, r.y));
+            x[2 * n1p + 1] = bfft::cmulc(make_float2(v.z, v.w), make_float2(r.z, r.w));
+          }
+          if (ch == 0 && kyl == 0)
+          {
+            // pack the Nyquist column into the (Hermitian) DC column: Z = X0 + i*X_{N/2}
+#pragma unroll
+            for (int n1p = 0; n1p < R1 / 2; n1p++)
+            {
+              const float4 r = ldg4(ref + L::MAIN4 + n1p * R2 + n2);
+              const float4 v = ldg4(conv + L::MAIN4 + n1p * R2 + n2);
+              const float2 t0 = bfft::cmulc(make_float2(v.x, v.y), make_float2(r.x, r.y));
+              const float2 t1 = bfft::cmulc(make_float2(v.z, v.w), make_float2(r.z, r.w));
+              x[2 * n1p].x -= t0.y;
+              x[2 * n1p].y += t0.x;
+              x[2 * n1p + 1].x -= t1.y;
+              x[2 * n1p + 1].y += t1.x;
+            }
+          }
+          bfft::Dft<R1, 1>::run(x);
+#pragma unroll
+          for (int k1 = 1; k1 < R1; k1++)
+            x[k1] = bfft::cmul(x[k1], TW[n2 * R1 + k1]);
+#pragma unroll
+          for (int k1 = 0; k1 < R1; k1++)
+            E[(k1 * R2 + n2) * KC + kyl] = x[k1];
+        }
+        __syncthreads();
+        for (int item = tid; item < R1 * KC; item += NT)
+        {
+          const int k1 = item / KC, kyl = item % KC;
+          float2 y[R2];
+#pragma unroll
+          for (int n2 = 0; n2 < R2; n2++)
+            y[n2] = E[(k1 * R2 + n2) * KC + kyl];
+          bfft::Dft<R2, 1>::run(y);
+#pragma unroll
+          for (int k2 = 0; k2 < R2; k2++)
+          {
+            const int w = WT[k1 + R1 * k2];
+            if (w != 255)
+              Y[(size_t) w * NCOL + ch * KC + kyl] = y[k2];
+          }
+        }
+        __syncthreads();
+      }
+
+      // ------------------------------------------------ row pass (along ky), 2 rows per transform
+      unsigned long long best = ~0ull;
+      float best_v = 0.f;
+      const int npairs = nwp / 2;
+      for (int p0 = 0; p0 < npairs; p0 += PC)
+      {
+        const int npl = min(PC, npairs - p0);
+        float2 x[R1];
+        const int pl1 = tid / R2, n2 = tid % R2;
+        const bool act1 = pl1 < npl;
+        float2 *Yp = Y + (size_t) (2 * (p0 + pl1)) * NCOL; // rows a,b contiguous: N complex
+        if (act1)
+        {
+          const float2 *Ya = Yp, *Yb = Yp + NCOL;
+#pragma unroll
+          for (int n1 = 0; n1 < R1; n1++)
+          {
+            if (n1 < R1 / 2)
+            {
+              const float2 a = Ya[n1 * R2 + n2], b = Yb[n1 * R2 + n2];
+              if (n1 == 0 && n2 == 0)
+                x[n1] = make_float2(a.x, b.x);
+              else
+                x[n1] = make_float2(a.x - b.y, a.y + b.x);
+            }
+            else
+            {
+              // n = n1*R2 + n2 >= N/2: mirrored element n' = N - n
+              const int nm = (R1 - n1) * R2 - n2;
+              if (n1 == R1 / 2 && n2 == 0)
+              {
+                const float2 a = Ya[0], b = Yb[0];
+                x[n1] = make_float2(a.y, b.y); // Nyquist, packed in the DC slot's imaginary part
+              }
+              else
+              {
+                const float2 a = Ya[nm], b = Yb[nm];
+                x[n1] = make_float2(a.x + b.y, b.x - a.y);
+              }
+            }
+          }
+          bfft::Dft<R1, 1>::run(x);
+#pragma unroll
+          for (int k1 = 1; k1 < R1; k1++)
+            x[k1] = bfft::cmul(x[k1], TW[n2 * R1 + k1]);
+        }
+        __syncthreads(); // all reads of this chunk's rows are done: safe to overwrite in place
+        if (act1)
+        {
+#pragma unroll
+          for (int k1 = 0; k1 < R1; k1++)
+            Yp[k1 * R2 + ((n2 + k1) % R2)] = x[k1];
+        }
+        __syncthreads();
+        for (int item = tid; item < npl * R1; item += NT)
+        {
+          const int pl = item / R1, k1 = item % R1;
+          const float2 *Yq = Y + (size_t) (2 * (p0 + pl)) * NCOL;
+          float2 y[R2];
+#pragma unroll
+          for (int n2b = 0; n2b < R2; n2b++)
+            y[n2b] = Yq[k1 * R2 + ((n2b + k1) % R2)];
+          bfft::Dft<R2, 1>::run(y);
+          const int wa = 2 * (p0 + pl), wb = wa + 1;
+          const bool vb = wb < nw;
+#pragma unroll
+          for (int k2 = 0; k2 < R2; k2++)
+          {
+            const int wy = WT[k1 + R1 * k2];
+            if (wy != 255)
+            {
+              {
+                const float v = y[k2].x * p.invNN;
+                const float fe = __fsub_rn(__fsub_rn(__fadd_rn(__fmul_rn(Nt, __fsub_rn(f_a, __fmul_rn(v, v))), __fmul_rn(f_b, v)), f_c), f_d);
+                const int lin = wa * nw + wy;
+                FE[lin] = fe;
+                const unsigned long long key = ((unsigned long long) __float_as_uint(fe) << 32) | (unsigned) lin;
+                if (key < best)
+                {
+                  best = key;
+                  best_v = v;
+                }
+                if (p.dbg_values)
+                  p.dbg_values[((size_t) oc * p.M + m) * nw * nw + lin] = v;
+              }
+              if (vb)
+              {
+                const float v = y[k2].y * p.invNN;
+                const float fe = __fsub_rn(__fsub_rn(__fadd_rn(__fmul_rn(Nt, __fsub_rn(f_a, __fmul_rn(v, v))), __fmul_rn(f_b, v)), f_c), f_d);
+                const int lin = wb * nw + wy;
+                FE[lin] = fe;
+                const unsigned long long key = ((unsigned long long) __float_as_uint(fe) << 32) | (unsigned) lin;
+                if (key < best)
+                {
+                  best = key;
+                  best_v = v;
+                }
+                if (p.dbg_values)
+                  p.dbg_values[((size_t) oc * p.M + m) * nw * nw + lin] = v;
+              }
+            }
+          }
+        }
+      }
+
+      // ------------------------------------------------ reduce over the displacement window
+      unsigned long long wbest = best;
+#pragma unroll
+      for (int s = 16; s > 0; s >>= 1)
+      {
+        const unsigned long long o = shfl_xor_u64(wbest, s);
+        wbest = o < wbest ? o : wbest;
+      }
+      if (lane == 0)
+        atomicMin(&s_key[buf], wbest);
+      __syncthreads();
+      const unsigned long long kmin = s_key[buf];
+      const float fmin = __uint_as_float((unsigned) (kmin >> 32));
+      if (best == kmin)
+        s_winv[buf] = best_v;
+      const float inv = __fdiv_rn(1.0f, fmin);
+      float S = 0.f;
+      for (int i = tid; i < nw * nw; i += NT)
+      {
+        const float t = (FE[i] - fmin) * inv;
+        if (t < p.tcut)
+        {
+          // log1p(t) for tiny t >= 0
+          const float l = t * (1.f - t * (0.5f - t * (1.f / 3.f)));
+          S += __expf(p.acoef_f * l);
+        }
+      }
+#pragma unroll
+      for (int s = 16; s > 0; s >>= 1)
+        S += __shfl_xor_sync(0xffffffffu, S, s);
+      if (lane == 0)
+        s_wsum[buf][warp] = S;
+      __syncthreads();
+
+      // ------------------------------------------------ bookkeeping (bioem_algorithm.h:84-141)
+      if (tid == 0)
+      {
+        s_key[buf ^ 1] = ~0ull;
+        float Ssum = 0.f;
+#pragma unroll
+        for (int w = 0; w < NT / 32; w++)
+          Ssum += s_wsum[buf][w];
+        const double lp = p.acoef_d * log((double) fmin) + cp.Bterm;
+        const float lpf = (float) lp;
+        if (bk_Const < (double) lpf)
+        {
+          bk_Total = bk_Total * exp(bk_Const - (double) lpf) + (double) Ssum;
+          bk_Const = (double) lpf;
+          bk_lpf = lpf;
+          bk_o = p.o_base + ol;
+          bk_c = c;
+          bk_lin = (int) (kmin & 0xffffffffu);
+          bk_v = s_winv[buf];
+          bk_sC = cp.sumC;
+          bk_ssC = cp.sumsqC;
+        }
+        else
+          bk_Total += (double) Ssum * exp((double) lpf - bk_Const);
+        if (p.angles)
+        {
+          if (an_Const < (double) lpf)
+          {
+            an_Total = an_Total * exp(an_Const - (double) lpf) + (double) Ssum;
+            an_Const = (double) lpf;
+          }
+          else
+            an_Total += (double) Ssum * exp((double) lpf - an_Const);
+        }
+      }
+      buf ^= 1;
+    }
+    if (tid == 0 && p.angles)
+    {
+      ProbAngleOut a;
+      a.forAngles = an_Total;
+      a.ConstAngle = an_Const;
+      p.angles[(size_t) (p.o_base + ol) * p.M + m] = a;
+    }
+  }
+  if (tid == 0)
+  {
+    Running r;
+    r.Const = bk_Const;
+    r.Total = bk_Total;
+    r.lpf = bk_lpf;
+    r.orient = bk_o;
+    r.conv = bk_c;
+    r.lin = bk_lin;
+    r.v = bk_v;
+    r.sumC = bk_sC;
+    r.sumsqC = bk_ssC;
+    r.pad = 0;
+    p.partials[(size_t) g * p.M + m] = r;
+  }
+}
+
+// fold the per-group partials of one batch into the running per-image state, in
+// orientation order (strict '<' keeps the first maximum, bioem_algorithm.h:96)
+__global__ void merge_partials_kernel(const Running *__restrict__ partials, int NG, int M, Running *__restrict__ state)
+{
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M)
+    return;
+  Running s = state[m];
+  for (int g = 0; g < NG; g++)
+  {
+    const Running r = partials[(size_t) g * M + m];
+    if (r.Total <= 0.0 && r.Const <= kMinProb)
+      continue;
+    if (s.Const < r.Const)
+    {
+      const double T = s.Total * exp(s.Const - r.Const) + r.Total;
+      s = r;
+      s.Total = T;
+    }
+    else
+      s.Total += r.Total * exp(r.Const - s.Const);
+  }
+  state[m] = s;
+}
+
+__global__ void init_state_kernel(Running *state, int M)
+{
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M)
+    return;
+  Running s;
+  s.Const = kMinProb;
+  s.Total = 0.0;
+  s.lpf = 0.f;
+  s.orient = 0;
+  s.conv = 0;
+  s.lin = 0;
+  s.v = 0.f;
+  s.sumC = 0.f;
+  s.sumsqC = 0.f;
+  s.pad = 0;
+  state[m] = s;
+}
+
+__global__ void init_angles_kernel(ProbAngleOut *a, size_t n)
+{
+  const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  a[i].forAngles = 0.0;
+  a[i].ConstAngle = kMinProb;
+}
+
+// Running -> bioem_Probability_map (norm / mu as bioem_algorithm.h:106-111)
+__global__ void finalize_kernel(const Running *__restrict__ state, const float *__restrict__ sumRef, int M, int nw,
+                                int npos, int maxD, int Gs, float Ntotpi, ProbMapOut *__restrict__ out)
+{
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M)
+    return;
+  const Running s = state[m];
+  ProbMapOut o;
+  o.Total = s.Total;
+  o.Constoadd = s.Const;
+  o.max_prob_orient = s.orient;
+  o.max_prob_conv = s.conv;
+  if (s.Const <= kMinProb)
+  {
+    o.max_prob_cent_x = o.max_prob_cent_y = 0;
+    o.max_prob_norm = o.max_prob_mu = 0.f;
+  }
+  else
+  {
+    const int wx = s.lin / nw, wy = s.lin % nw;
+    // window index -> signed displacement in the reference's enumeration
+    // (0, G, .., maxD, then N-maxD, N-maxD+G, ... reported as negative; bioem_algorithm.h:156-197)
+    const int dx = wx < npos ? wx * Gs : (wx - npos) * Gs - maxD;
+    const int dy = wy < npos ? wy * Gs : (wy - npos) * Gs - maxD;
+    o.max_prob_cent_x = -dx;
+    o.max_prob_cent_y = -dy;
+    const float sR = sumRef[m];
+    const float den = __fsub_rn(__fmul_rn(s.sumC, s.sumC), __fmul_rn(s.sumsqC, Ntotpi));
+    o.max_prob_norm = __fdiv_rn(-__fadd_rn(__fmul_rn(-s.sumC, sR), __fmul_rn(Ntotpi, s.v)), den);
+    o.max_prob_mu = __fdiv_rn(-__fadd_rn(__fmul_rn(-s.sumC, s.v), __fmul_rn(s.sumsqC, sR)), den);
+  }
+  out[m] = o;
+}
+
+} // namespace bioem

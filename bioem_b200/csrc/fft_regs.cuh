@@ -1,0 +1,282 @@
+// In-register DFT building blocks for the sm_100a kernels.
+//
+// Every transform of length N = R1 * R2 in this library is a two-pass Stockham
+// decomposition: radix-R1 butterflies held entirely in registers, one twiddle
+// multiply, ONE shared-memory exchange, radix-R2 butterflies in registers.  The
+// radix-R butterflies below are built at compile time from small prime kernels
+// (2, 4, odd primes by the symmetric-pair formula); all internal twiddles are
+// compile-time constants produced by an exact-octant constexpr sin/cos, so they
+// become FFMA immediates.
+#pragma once
+#include <cuda_runtime.h>
+#include <type_traits>
+
+#define BFFT_HD __host__ __device__
+
+namespace bfft
+{
+
+// ---------------------------------------------------------------- constexpr trig
+constexpr double kPi = 3.14159265358979323846264338327950288;
+
+BFFT_HD constexpr double sin_taylor(double x) // |x| <= pi/4
+{
+  double x2 = x * x, term = x, sum = x;
+  for (int k = 1; k < 14; k++)
+  {
+    term *= -x2 / ((2.0 * k) * (2.0 * k + 1.0));
+    sum += term;
+  }
+  return sum;
+}
+BFFT_HD constexpr double cos_taylor(double x) // |x| <= pi/4
+{
+  double x2 = x * x, term = 1.0, sum = 1.0;
+  for (int k = 1; k < 14; k++)
+  {
+    term *= -x2 / ((2.0 * k - 1.0) * (2.0 * k));
+    sum += term;
+  }
+  return sum;
+}
+struct cs_t
+{
+  double c, s;
+};
+// exp(2*pi*i * p / q) with exact symmetry reduction (exact 0 / +-1 where due)
+BFFT_HD constexpr cs_t unit_root(long long p, long long q)
+{
+  p %= q;
+  if (p < 0)
+    p += q;
+  // work in units of 1/(8q) turns: a = 8p in [0, 8q)
+  bool conj = false, negc = false, swap = false;
+  long long num = p, den = q; // angle = 2*pi*num/den, num/den in [0,1)
+  if (2 * num > den)
+  { // > half turn: conj symmetry
+    num = den - num;
+    conj = true;
+  }
+  if (4 * num > den)
+  { // > quarter: cos -> -cos of (1/2 - f)
+    num = den - 2 * num; // over 2*den
+    den = 2 * den;
+    negc = true;
+  }
+  if (8 * num > den)
+  { // > eighth: swap sin/cos of (1/4 - f)
+    num = den - 4 * num; // over 4*den
+    den = 4 * den;
+    swap = true;
+  }
+  double ang = 2.0 * kPi * (double) num / (double) den;
+  double c = cos_taylor(ang), s = sin_taylor(ang);
+  if (num == 0)
+  {
+    c = 1.0;
+    s = 0.0;
+  }
+  if (swap)
+  {
+    double t = c;
+    c = s;
+    s = t;
+  }
+  if (negc)
+    c = -c;
+  if (conj)
+    s = -s;
+  return cs_t{c, s};
+}
+
+// ---------------------------------------------------------------- helpers
+template <int I, int E, class F> BFFT_HD __forceinline__ void static_for(F &&f)
+{
+  if constexpr (I < E)
+  {
+    f(std::integral_constant<int, I>{});
+    static_for<I + 1, E>(f);
+  }
+}
+
+BFFT_HD __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+BFFT_HD __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+BFFT_HD __forceinline__ float2 cmul(float2 a, float2 b)
+{
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+// a * conj(b)
+BFFT_HD __forceinline__ float2 cmulc(float2 a, float2 b)
+{
+  return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+
+// multiply by the compile-time constant exp(SIGN * 2*pi*i * P / Q)
+template <int SIGN, int P, int Q> BFFT_HD __forceinline__ float2 cmul_root(float2 a)
+{
+  constexpr cs_t w = unit_root((long long) SIGN * P, Q);
+  constexpr float c = (float) w.c, s = (float) w.s;
+  if constexpr (w.s == 0.0 && w.c == 1.0)
+    return a;
+  else if constexpr (w.s == 0.0 && w.c == -1.0)
+    return make_float2(-a.x, -a.y);
+  else if constexpr (w.c == 0.0 && w.s == 1.0)
+    return make_float2(-a.y, a.x);
+  else if constexpr (w.c == 0.0 && w.s == -1.0)
+    return make_float2(a.y, -a.x);
+  else
+    return make_float2(a.x * c - a.y * s, a.x * s + a.y * c);
+}
+
+BFFT_HD constexpr int pick_factor(int r)
+{
+  if (r % 4 == 0 && r > 4)
+    return 4;
+  if (r % 2 == 0 && r > 2)
+    return 2;
+  for (int p = 3; p * p <= r; p += 2)
+    if (r % p == 0)
+      return p;
+  return r; // prime
+}
+
+// ---------------------------------------------------------------- butterflies
+// Dft<R, SIGN>::run(v): in-place DFT of v[0..R), natural order in and out,
+// X[k] = sum_n v[n] exp(SIGN * 2*pi*i * n*k / R).
+template <int R, int SIGN, int A = pick_factor(R)> struct Dft;
+
+template <int SIGN> struct Dft<1, SIGN, 1>
+{
+  BFFT_HD __forceinline__ static void run(float2 *) {}
+};
+
+template <int SIGN> struct Dft<2, SIGN, 2>
+{
+  BFFT_HD __forceinline__ static void run(float2 *v)
+  {
+    float2 a = v[0], b = v[1];
+    v[0] = cadd(a, b);
+    v[1] = csub(a, b);
+  }
+};
+
+template <int SIGN> struct Dft<4, SIGN, 4>
+{
+  BFFT_HD __forceinline__ static void run(float2 *v)
+  {
+    float2 t0 = cadd(v[0], v[2]), t1 = csub(v[0], v[2]);
+    float2 t2 = cadd(v[1], v[3]), d = csub(v[1], v[3]);
+    // (SIGN*i) * d
+    float2 t3 = make_float2(-SIGN * d.y, SIGN * d.x);
+    v[0] = cadd(t0, t2);
+    v[1] = cadd(t1, t3);
+    v[2] = csub(t0, t2);
+    v[3] = csub(t1, t3);
+  }
+};
+
+// odd prime R: symmetric-pair formula
+template <int R, int SIGN> struct Dft<R, SIGN, R>
+{
+  static_assert(R % 2 == 1 && R >= 3, "prime kernel expects an odd prime");
+  BFFT_HD __forceinline__ static void run(float2 *v)
+  {
+    constexpr int H = (R - 1) / 2;
+    float2 s[H + 1], d[H + 1];
+    float2 x0 = v[0];
+    float2 sum = x0;
+    static_for<1, H + 1>([&](auto k_) {
+      constexpr int k = decltype(k_)::value;
+      s[k] = cadd(v[k], v[R - k]);
+      d[k] = csub(v[k], v[R - k]);
+      sum = cadd(sum, s[k]);
+    });
+    v[0] = sum;
+    static_for<1, H + 1>([&](auto j_) {
+      constexpr int j = decltype(j_)::value;
+      float2 m = x0;
+      float2 e = make_float2(0.f, 0.f);
+      static_for<1, H + 1>([&](auto k_) {
+        constexpr int k = decltype(k_)::value;
+        constexpr cs_t w = unit_root((long long) j * k, R);
+        constexpr float c = (float) w.c, sn = (float) (SIGN * w.s);
+        m.x = fmaf(c, s[k].x, m.x);
+        m.y = fmaf(c, s[k].y, m.y);
+        e.x = fmaf(sn, d[k].x, e.x);
+        e.y = fmaf(sn, d[k].y, e.y);
+      });
+      // X_j = m + i*e ; X_{R-j} = m - i*e
+      v[j] = make_float2(m.x - e.y, m.y + e.x);
+      v[R - j] = make_float2(m.x + e.y, m.y - e.x);
+    });
+  }
+};
+
+// composite R = A * B (A = pick_factor(R)):
+//   n = n1*B + n2, k = k1 + A*k2
+//   X[k1 + A*k2] = sum_{n2} W_R^{n2*k1} W_B^{n2*k2} sum_{n1} x[n1*B+n2] W_A^{n1*k1}
+template <int R, int SIGN, int A> struct Dft
+{
+  static_assert(R % A == 0 && A > 1 && A < R, "bad factorisation");
+  BFFT_HD __forceinline__ static void run(float2 *v)
+  {
+    constexpr int B = R / A;
+    float2 t[R]; // t[k1*B + n2]
+    static_for<0, B>([&](auto n2_) {
+      constexpr int n2 = decltype(n2_)::value;
+      float2 a[A];
+      static_for<0, A>([&](auto n1_) {
+        constexpr int n1 = decltype(n1_)::value;
+        a[n1] = v[n1 * B + n2];
+      });
+      Dft<A, SIGN>::run(a);
+      static_for<0, A>([&](auto k1_) {
+        constexpr int k1 = decltype(k1_)::value;
+        t[k1 * B + n2] = cmul_root<SIGN, n2 * k1, R>(a[k1]);
+      });
+    });
+    static_for<0, A>([&](auto k1_) {
+      constexpr int k1 = decltype(k1_)::value;
+      float2 b[B];
+      static_for<0, B>([&](auto n2_) {
+        constexpr int n2 = decltype(n2_)::value;
+        b[n2] = t[k1 * B + n2];
+      });
+      Dft<B, SIGN>::run(b);
+      static_for<0, B>([&](auto k2_) {
+        constexpr int k2 = decltype(k2_)::value;
+        v[k1 + A * k2] = b[k2];
+      });
+    });
+  }
+};
+
+// ---------------------------------------------------------------- geometry
+// Two-pass split N = R1 * R2 and tiling constants for the supported image edges.
+//   KC  packed spectrum columns per column-pass chunk (NCOL = N/2 must divide)
+//   PC  row pairs per row-pass chunk
+template <int N> struct Geo;
+#define BFFT_GEO(N_, R1_, R2_, KC_, PC_)                                                           \
+  template <> struct Geo<N_>                                                                       \
+  {                                                                                                \
+    static constexpr int R1 = R1_, R2 = R2_, KC = KC_, PC = PC_;                                   \
+    static_assert(R1_ * R2_ == N_ && (R1_ % 2) == 0 && ((N_ / 2) % KC_) == 0, "geometry");         \
+  };
+BFFT_GEO(32, 4, 8, 16, 16)
+BFFT_GEO(36, 6, 6, 18, 16)
+BFFT_GEO(48, 6, 8, 12, 16)
+BFFT_GEO(64, 8, 8, 16, 16)
+BFFT_GEO(96, 8, 12, 16, 16)
+BFFT_GEO(128, 8, 16, 16, 16)
+BFFT_GEO(160, 10, 16, 16, 16)
+BFFT_GEO(192, 12, 16, 16, 16)
+BFFT_GEO(224, 14, 16, 16, 16)
+BFFT_GEO(256, 16, 16, 16, 16)
+BFFT_GEO(288, 18, 16, 16, 12)
+BFFT_GEO(320, 20, 16, 16, 12)
+BFFT_GEO(360, 18, 20, 20, 12)
+BFFT_GEO(384, 16, 24, 16, 10)
+BFFT_GEO(400, 20, 20, 20, 12)
+#undef BFFT_GEO
+
+} // namespace bfft

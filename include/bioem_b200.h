@@ -1,0 +1,179 @@
+/* bioem_b200 — C ABI of the B200-native BioEM likelihood path.
+ *
+ * This is the drop-in boundary for the reference's per-orientation likelihood
+ * pipeline.  In the reference the seam is the C++ virtual interface of class bioem
+ * (reference include/bioem.h:52-59,76-79: compareRefMaps / deviceInit / deviceStartRun
+ * / deviceFinishRun / malloc_device_host) behind the factory bioem_cuda_create()
+ * (reference include/bioem_cuda.h:20).  Because this library also moves projection
+ * and CTF convolution onto the GPU, the seam sits one level higher: the host hands
+ * over the inputs once and then asks for a RANGE OF ORIENTATIONS to be evaluated
+ * against all particle images; results come back in the reference's own result
+ * structs (bioem_Probability_map / bioem_Probability_angle).
+ *
+ * Conventions: plain C types only; every function returns 0 on success and a
+ * non-zero code on failure, with a message available from bioem_b200_last_error()
+ * (the reference itself prints and exit(1)s, defs.h:18-26 — the host binary keeps
+ * doing that on a non-zero return).  The library copies all inputs at upload time;
+ * the caller keeps ownership of every pointer it passes.  A handle is bound to one
+ * CUDA device and must be driven by one host thread at a time; handles are
+ * independent.  There is no CPU fallback: without a usable CUDA device every
+ * device entry point fails.
+ */
+#ifndef BIOEM_B200_H
+#define BIOEM_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BIOEM_B200_OK 0
+#define BIOEM_B200_ERR_INVALID 1 /* bad argument / unsupported size   */
+#define BIOEM_B200_ERR_CUDA 2    /* CUDA runtime failure              */
+#define BIOEM_B200_ERR_STATE 3   /* call order violated               */
+
+typedef struct bioem_b200_context *bioem_b200_handle;
+
+/* Replaces bioem_param_device (reference include/param.h:26-47) plus the four host
+ * parameters createProjection reads (pixelSize, shiftX, shiftY, doquater;
+ * reference bioem.cpp:1627,1715-1750). */
+typedef struct bioem_b200_config
+{
+  int NumberPixels;      /* N, even; supported: 32 36 48 64 96 128 160 192 224 256 288 320 360 384 400 */
+  int maxDisplaceCenter; /* DISPLACE_CENTER first value  */
+  int GridSpaceCenter;   /* DISPLACE_CENTER second value; must divide maxDisplaceCenter */
+  int writeAngles;       /* WRITE_PROB_ANGLES (0 = off)  */
+  int tousepsf;          /* USE_PSF                       */
+  int doquater;          /* orientations are quaternions  */
+  int shiftX, shiftY;    /* SHIFT_X / SHIFT_Y             */
+  float pixelSize;
+  float Ntotpi; /* (float)(N*N), reference param.cpp:1612 */
+  float volu;   /* reference param.cpp:1600-1607 (only used by the caller's output stage) */
+  float sigmaPriorbctf, sigmaPriordefo, Priordefcent, sigmaPrioramp, Priorampcent;
+} bioem_b200_config;
+
+/* == bioem_Probability_map (reference include/map.h:116-129), 40 bytes */
+typedef struct bioem_b200_prob_map
+{
+  double Total;
+  double Constoadd;
+  int max_prob_cent_x, max_prob_cent_y, max_prob_orient, max_prob_conv;
+  float max_prob_norm, max_prob_mu;
+} bioem_b200_prob_map;
+
+/* == bioem_Probability_angle (reference include/map.h:131-135), 16 bytes */
+typedef struct bioem_b200_prob_angle
+{
+  double forAngles;
+  double ConstAngle;
+} bioem_b200_prob_angle;
+
+/* == bioem_model::bioem_model_point (reference include/model.h:179-185), 24 bytes */
+typedef struct bioem_b200_model_point
+{
+  float pos[3];
+  float quat4; /* padding in the reference's myfloat3_t */
+  float radius;
+  float density;
+} bioem_b200_model_point;
+
+const char *bioem_b200_last_error(void);
+int bioem_b200_version(void);
+/* number of visible CUDA devices (0 when there is none; never an error) */
+int bioem_b200_device_count(void);
+/* 1 if N is an image edge the kernels are instantiated for */
+int bioem_b200_supported_size(int NumberPixels);
+
+/* replaces bioem_cuda_create() + deviceInit() (reference bioem_cuda.cu:818-911) */
+int bioem_b200_create(const bioem_b200_config *cfg, int device, bioem_b200_handle *out);
+int bioem_b200_destroy(bioem_b200_handle h);
+
+/* Model.points / Model.NormDen (reference model.h, bioem.cpp:1677-1810) */
+int bioem_b200_upload_model(bioem_b200_handle h, const bioem_b200_model_point *points, int nPoints,
+                            float NormDen);
+/* param.angles: nOrient x myfloat3_t {pos[3], quat4} (reference param.h, defs.h:105-110) */
+int bioem_b200_upload_orientations(bioem_b200_handle h, const float *angles4, int nOrient);
+/* param.refCTF (nCtf x N x (N/2+1) interleaved complex, reference param.cpp:1359) and
+ * param.CtfParam (nCtf x myfloat3_t {amp, phase, env, -}) */
+int bioem_b200_upload_ctf(bioem_b200_handle h, const float *refCTF, const float *CtfParam4, int nCtf);
+/* RefMap.maps (nMaps x N x N, as read, BEFORE RefMap.precalculate): the library
+ * computes sum_RefMap / sumsquare_RefMap / RefMapsFFT itself (replaces reference
+ * map.cpp:557-630). */
+int bioem_b200_upload_particles(bioem_b200_handle h, const float *maps, int nMaps);
+/* alternative: the caller already ran RefMap.precalculate (RefMapsFFT nMaps x N x
+ * (N/2+1) complex, sum_RefMap, sumsquare_RefMap) */
+int bioem_b200_upload_particles_fft(bioem_b200_handle h, const float *RefMapsFFT, const float *sum_RefMap,
+                                    const float *sumsquare_RefMap, int nMaps);
+
+/* replaces the initialisation loop of bioem::run (reference bioem.cpp:681-699) */
+int bioem_b200_reset(bioem_b200_handle h);
+/* replaces the main loop of bioem::run (reference bioem.cpp:763-891) for orientations
+ * [oBegin, oEnd): projection, convolution with every CTF, comparison with every
+ * particle.  Asynchronous; results accumulate on the device across calls. */
+int bioem_b200_run(bioem_b200_handle h, int oBegin, int oEnd);
+int bioem_b200_synchronize(bioem_b200_handle h);
+/* replaces deviceFinishRun's copy-back (reference bioem_cuda.cu:1017-1021):
+ * maps_out[nMaps]; angles_out[nOrient*nMaps] in the reference's layout
+ * angle*nMaps+map (map.h:147-150), may be NULL when writeAngles == 0. */
+int bioem_b200_download(bioem_b200_handle h, bioem_b200_prob_map *maps_out, bioem_b200_prob_angle *angles_out);
+
+/* Multi-GPU (replaces the MPI reduction, reference bioem.cpp:909-1044).  Each GPU
+ * runs a contiguous block of orientations; the per-image partial results are
+ * exported as an opaque device blob of bioem_b200_partial_bytes(h) bytes, gathered
+ * from all ranks by the caller (one all-gather, e.g. ncclAllGather), and imported in
+ * rank order.  Ties between ranks resolve to the LOWEST rank (= lowest orientation
+ * index, like a 1-process run). */
+size_t bioem_b200_partial_bytes(bioem_b200_handle h);
+int bioem_b200_export_partial(bioem_b200_handle h, void *device_dst);
+int bioem_b200_import_partials(bioem_b200_handle h, const void *device_gathered, int nRanks);
+/* same merge on host buffers (used by the single-process multi-GPU host binary) */
+int bioem_b200_merge_host(const bioem_b200_prob_map *parts, int nRanks, int nMaps, bioem_b200_prob_map *out);
+/* the stream all work of this handle is enqueued on (a cudaStream_t) */
+void *bioem_b200_stream(bioem_b200_handle h);
+/* device pointer to the [nOrient][nMaps] angle table (NULL when writeAngles == 0) */
+void *bioem_b200_device_angles(bioem_b200_handle h);
+
+/* statistics of the last run() calls since reset(): kernels launched, likelihoods */
+int bioem_b200_stats(bioem_b200_handle h, long long *kernel_launches, long long *likelihoods);
+/* cudaEvent-timed duration [ms] of all fused likelihood kernels since reset() and
+ * their launch count (for roofline accounting); synchronises the stream */
+int bioem_b200_kernel_time(bioem_b200_handle h, double *likelihood_ms, long long *likelihood_launches);
+
+/* ---- inspection entry points (tests): intermediate products of one orientation ---- */
+/* real-space projection (N*N, already scaled by NormDen/tempden) */
+int bioem_b200_debug_projection(bioem_b200_handle h, int iOrient, float *proj_out);
+/* convolved map in the reference's N x (N/2+1) interleaved complex layout + sumC, sumsquareC */
+int bioem_b200_debug_convolved(bioem_b200_handle h, int iOrient, int iConv, float *conv_out, float *sumC,
+                               float *sumsquareC);
+/* correlation values lCC/N^2 over the displacement window of (iOrient, iConv, iMap),
+ * in doRefMapFFT enumeration order (reference bioem_algorithm.h:156-197) */
+int bioem_b200_debug_correlation(bioem_b200_handle h, int iOrient, int iConv, int iMap, float *values_out,
+                                 int *nValues);
+/* particle spectrum in the reference layout + its sums */
+int bioem_b200_debug_particle(bioem_b200_handle h, int iMap, float *fft_out, float *sum, float *sumsq);
+
+/* ---- host-side input preparation (pure CPU; mirrors the reference's one-off setup) ---- */
+/* param.cpp:601-607 */
+void bioem_b200_host_defocus_to_phase(float startDefocus, float endDefocus, float elecwavel, float *startPhase,
+                                      float *endPhase, float *Priordefcent, float *sigmaPriordefo);
+/* param.cpp:1336-1620 CalculateRefCTF (CTF mode and PSF mode); returns nCtf.  refCTF / CtfParam4 may
+ * be NULL to query the count and the grid steps (grids[3] = amp, phase, envelope step). */
+int bioem_b200_host_ctf_table(int N, float pixelSize, int usepsf, float startAmp, float endAmp, int nAmp,
+                              float startPhase, float endPhase, int nPhase, float startEnv, float endEnv,
+                              int nEnv, float *refCTF, float *CtfParam4, float *grids);
+/* param.cpp:1600-1607 */
+float bioem_b200_host_volu(float voluang, int GridSpaceCenter, float pixelSize, int maxDisplaceCenter,
+                           int nAmp, float gridEnvelop, float gridCTF_phase, float sigmaPriorbctf,
+                           float sigmaPriordefo, float sigmaPrioramp);
+/* model.cpp:604-672 (centre of density) and NormDen; points modified in place; returns NormDen */
+float bioem_b200_host_model_prepare(bioem_b200_model_point *points, int nPoints, int center);
+/* map.cpp:830-845: the MRC reader's per-image normalisation (in place, N*N) */
+void bioem_b200_host_normalise_map(float *img, int N);
+/* bioem.cpp:1144-1149: final log posterior of one image */
+double bioem_b200_host_final_logprob(const bioem_b200_config *cfg, double Total, double Constoadd);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

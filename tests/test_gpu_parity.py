@@ -1,0 +1,240 @@
+"""GPU parity tests: the sm_100a path, called through the C ABI (bioem_b200.api -> ctypes ->
+libbioem_b200.so), against the CPU oracle on the same seeded inputs and against the committed
+outputs of the unmodified reference binary (tests/golden).  Nothing here reads /root/reference.
+
+Tolerances (floating point path, north_star: log P within 1e-4 relative, arg-max identical
+except documented near-ties):
+  * per-image log P:        |gpu - oracle| <= LOGP_ATOL[N]  (and always <= 1e-4 * |log P|)
+  * arg-max (orient, conv, cent_x, cent_y): identical, or the oracle's own float-narrowed
+    logpro at the GPU's choice is within NEAR_TIE[N] of the oracle's maximum (near-tie)
+  * stage outputs: relative to the stage's own magnitude, a few float ulps times log2(N)
+"""
+import os
+
+import numpy as np
+import pytest
+
+from bioem_b200 import api
+from bioem_b200.cases import build_case
+from bioem_b200.outputs import parse_output_probabilities
+from oracle import pyoracle
+
+pytestmark = pytest.mark.gpu
+
+LOGP_ATOL = {32: 5e-3, 36: 5e-3, 64: 2e-2, 128: 5e-2, 224: 0.3, 360: 1.0}
+NEAR_TIE = LOGP_ATOL
+
+
+def _need_gpu():
+    if api.lib().bioem_b200_device_count() == 0:
+        pytest.fail("no CUDA device visible: the gpu-marked tests must run on the B200 box")
+
+
+@pytest.fixture(scope="module")
+def setups():
+    _need_gpu()
+    cache = {}
+
+    def get(name, **kw):
+        key = (name, tuple(sorted(kw.items())))
+        if key not in cache:
+            cd = build_case(name, **kw)
+            hi, parts = api.inputs_for_case(cd)
+            eng = api.Engine(hi.cfg)
+            eng.upload_all(hi, parts)
+            P = pyoracle.Prepared(cd.case, cd.model, cd.quats, cd.particles)
+            cache[key] = (cd, hi, parts, eng, P)
+        return cache[key]
+
+    yield get
+    for v in cache.values():
+        v[3].close()
+
+
+@pytest.mark.parametrize("name", ["toy32", "toy36g2", "toy64", "cfg1", "cfg2_slice", "cfg4_slice"])
+def test_stage1_projection_matches_oracle(setups, name):
+    cd, hi, parts, eng, P = setups(name)
+    for o in (0, P.O - 1):
+        _, want = P.projection(o, want_real=True)
+        got = eng.debug_projection(o)
+        scale = np.abs(want).max()
+        assert np.abs(got - want).max() <= 2e-6 * scale, (o, np.abs(got - want).max(), scale)
+        # pixels that receive density are the same pixels
+        assert ((got != 0) == (want != 0)).all()
+
+
+@pytest.mark.parametrize("name", ["toy32", "toy36g2", "toy64", "cfg1", "cfg2_slice", "cfg4_slice"])
+def test_stage2_convolution_matches_oracle(setups, name):
+    cd, hi, parts, eng, P = setups(name)
+    n = cd.case.n_pixels
+    for o, c in ((0, 0), (P.O - 1, P.C - 1)):
+        want, s, ss = P.convolve(P.projection(o), c)
+        got, gs, gss = eng.debug_convolved(o, c)
+        scale = np.abs(want).max()
+        assert np.abs(got - want).max() <= 4e-7 * np.log2(n * n) * scale
+        assert abs(gs - s) <= 2e-6 * abs(s)
+        assert abs(gss - ss) <= 2e-5 * abs(ss)
+
+
+@pytest.mark.parametrize("name", ["toy32", "toy36g2", "toy64", "cfg1", "cfg2_slice", "cfg4_slice"])
+def test_particle_precompute_matches_oracle(setups, name):
+    cd, hi, parts, eng, P = setups(name)
+    n = cd.case.n_pixels
+    for m in (0, P.M - 1):
+        got, s, ss = eng.debug_particle(m)
+        want = P.RefMapsFFT[m]
+        scale = np.abs(want).max()
+        assert np.abs(got - want).max() <= 4e-7 * np.log2(n * n) * scale
+        # sums are accumulated in the reference's sequential float order: bit-exact
+        assert s == P.sumRef[m] and ss == P.sumsqRef[m]
+
+
+def _window(P):
+    c = P.case
+    N, maxd, G = c.n_pixels, c.max_disp, c.grid_space
+    return list(range(0, maxd + 1, G)) + list(range(N - maxd, N, G))
+
+
+@pytest.mark.parametrize("name", ["toy32", "toy36g2", "toy64", "cfg1", "cfg2_slice", "cfg4_slice"])
+def test_stage3_correlation_window_matches_oracle(setups, name):
+    cd, hi, parts, eng, P = setups(name)
+    n = cd.case.n_pixels
+    xs = _window(P)
+    for o, c, m in ((0, 0, 0), (P.O - 1, P.C - 1, P.M - 1)):
+        conv, s, ss = P.convolve(P.projection(o), c)
+        cc = P.cross_correlation(conv, m) / np.float32(n * n)
+        want = cc[np.ix_(xs, xs)]
+        got = eng.debug_correlation(o, c, m)
+        # error of an FFT output is relative to the rms of the whole map, not to the entry
+        scale = np.sqrt((cc.astype(np.float64) ** 2).mean()) * np.sqrt(n)
+        assert np.abs(got - want).max() <= 3e-6 * max(scale, np.abs(want).max()), \
+            (np.abs(got - want).max(), scale, np.abs(want).max())
+
+
+def _compare_with_oracle(P, hi, pm, res, n):
+    atol = LOGP_ATOL[n]
+    near = []
+    for m in range(P.M):
+        g, o = pm[m], res["prob"][m]
+        lg = hi.final_logprob(g["Total"], g["Constoadd"])
+        lo = P.final_logprob(o["Total"], o["Constoadd"])
+        assert abs(lg - lo) <= atol, (m, lg, lo)
+        assert abs(lg - lo) <= 1e-4 * abs(lo)
+        same = all(g[k] == o[k] for k in ("orient", "conv", "cent_x", "cent_y"))
+        if same:
+            assert abs(g["Constoadd"] - o["Constoadd"]) <= atol
+            assert abs(g["norm"] - o["norm"]) <= 1e-3 * abs(o["norm"]) + 1e-6
+            assert abs(g["mu"] - o["mu"]) <= 1e-3 * abs(o["mu"]) + 1e-5
+        else:
+            lp_at = P.logpro_at(m, int(g["orient"]), int(g["conv"]), int(g["cent_x"]), int(g["cent_y"]))
+            assert o["Constoadd"] - lp_at <= NEAR_TIE[n], ("not a near-tie", m, g, o, lp_at)
+            near.append(m)
+    return near
+
+
+@pytest.mark.parametrize("name", ["toy32", "toy36g2", "toy64", "cfg1", "cfg2_slice", "cfg4_slice"])
+def test_full_run_matches_oracle(setups, name):
+    cd, hi, parts, eng, P = setups(name)
+    eng.reset()
+    eng.run()
+    pm, pa = eng.download()
+    res = P.run()
+    near = _compare_with_oracle(P, hi, pm, res, cd.case.n_pixels)
+    assert len(near) <= max(1, P.M // 3), near
+
+
+@pytest.mark.parametrize("name", ["toy32", "toy64", "cfg1", "cfg2_slice"])
+def test_full_run_matches_reference_golden(setups, name, golden_dir):
+    cd, hi, parts, eng, P = setups(name)
+    ref = parse_output_probabilities(os.path.join(golden_dir, name, "Output_Probabilities"))
+    eng.reset()
+    eng.run()
+    pm, _ = eng.download()
+    atol = LOGP_ATOL[cd.case.n_pixels]
+    for m in range(P.M):
+        g = pm[m]
+        lg = hi.final_logprob(g["Total"], g["Constoadd"])
+        assert abs(lg - ref["logp"][m]) <= atol + 1e-4
+        assert abs(lg - ref["logp"][m]) <= 1e-4 * abs(ref["logp"][m])
+        same = (g["cent_x"] == ref["cent_x"][m] and g["cent_y"] == ref["cent_y"][m]
+                and np.allclose(hi.angles[g["orient"]], ref["angles"][m], atol=1.1e-4)
+                and abs(hi.CtfParam[g["conv"], 2] - ref["env"][m]) < 1.1e-4)
+        if not same:
+            lp_at = P.logpro_at(m, int(g["orient"]), int(g["conv"]), int(g["cent_x"]), int(g["cent_y"]))
+            assert ref["const"][m] - lp_at <= NEAR_TIE[cd.case.n_pixels] + 1e-4
+
+
+@pytest.mark.parametrize("name", ["toy32", "cfg5_slice"])
+def test_angle_table_matches_oracle(setups, name):
+    cd, hi, parts, eng, P = setups(name)
+    eng.reset()
+    eng.run()
+    pm, pa = eng.download()
+    res = P.run()
+    assert pa is not None and pa.shape == (P.O, P.M)
+    atol = LOGP_ATOL[cd.case.n_pixels]
+    for m in range(P.M):
+        for o in range(P.O):
+            lg = hi.final_logprob(pa[o, m]["forAngles"], pa[o, m]["ConstAngle"])
+            lo = P.final_logprob(res["angle"][o, m]["forAngles"], res["angle"][o, m]["ConstAngle"])
+            assert abs(lg - lo) <= atol, (m, o, lg, lo)
+
+
+def test_split_runs_accumulate_and_partials_roundtrip(setups):
+    """Size-independent properties: evaluating [0,a) then [a,O) equals one call; results are
+    deterministic; merging per-block results on the host equals the single run."""
+    cd, hi, parts, eng, P = setups("toy64")
+    eng.reset()
+    eng.run()
+    full, _ = eng.download()
+    eng.reset()
+    eng.run()
+    again, _ = eng.download()
+    assert full.tobytes() == again.tobytes()  # bit-deterministic
+    eng.reset()
+    eng.run(0, 13)
+    eng.run(13, P.O)
+    split, _ = eng.download()
+    np.testing.assert_allclose(split["Total"], full["Total"], rtol=1e-12)
+    for k in ("Constoadd", "cent_x", "cent_y", "orient", "conv", "norm", "mu"):
+        np.testing.assert_array_equal(split[k], full[k])
+    blocks = []
+    for a, b in ((0, 7), (7, 20), (20, P.O)):
+        eng.reset()
+        eng.run(a, b)
+        blocks.append(eng.download()[0])
+    merged = api.merge_host(np.stack(blocks))
+    np.testing.assert_allclose(merged["Total"], full["Total"], rtol=1e-12)
+    for k in ("Constoadd", "cent_x", "cent_y", "orient", "conv", "norm", "mu"):
+        np.testing.assert_array_equal(merged[k], full[k])
+
+
+def test_particle_upload_paths_agree(setups):
+    """upload_particles (device FFT) and upload_particles_fft (host-provided spectra) give the
+    same result up to FFT rounding."""
+    cd, hi, parts, eng, P = setups("toy64")
+    eng.reset()
+    eng.run()
+    a, _ = eng.download()
+    e2 = api.Engine(hi.cfg)
+    e2.upload_model(hi.points, hi.NormDen)
+    e2.upload_orientations(hi.angles)
+    e2.upload_ctf(hi.refCTF, hi.CtfParam)
+    e2.upload_particles_fft(P.RefMapsFFT, P.sumRef, P.sumsqRef)
+    e2.run()
+    b, _ = e2.download()
+    e2.close()
+    for m in range(P.M):
+        assert abs(hi.final_logprob(a[m]["Total"], a[m]["Constoadd"])
+                   - hi.final_logprob(b[m]["Total"], b[m]["Constoadd"])) <= LOGP_ATOL[64]
+
+
+def test_recovers_planted_parameters(setups):
+    """The synthetic particles carry a known orientation / displacement: at SNR 0.1 most images
+    must recover the planted orientation index."""
+    cd, hi, parts, eng, P = setups("toy64")
+    eng.reset()
+    eng.run()
+    pm, _ = eng.download()
+    hit = sum(int(pm[m]["orient"] == cd.truth[m, 0]) for m in range(P.M))
+    assert hit >= P.M - 2, (pm["orient"], cd.truth[:, 0])
