@@ -505,13 +505,48 @@ __global__ void __launch_bounds__(NT) ctf_conv_kernel(const float4 *__restrict__
     v.y = a.y * k.x - a.x * k.y;
     v.z = a.z * k.z + a.w * k.w;
     v.w = a.w * k.z - a.z * k.w;
-    V[i] = v;
     // Hermitian weights (bioem.cpp:1893-1914): 1 for ky = 0 and ky = N/2, else 2
     float w = 2.f;
-    if (i >= L::MAIN4)
+    const bool tail = i >= L::MAIN4;
+    const bool dc = !tail && (i % L::KC) == 0 && (i / (L::KC * L::R2 * (L::R1 / 2))) == 0;
+    if (tail || dc)
       w = 1.f;
-    else if ((i % L::KC) == 0 && (i / (L::KC * L::R2 * (L::R1 / 2))) == 0)
-      w = 1.f;
+    float4 vs = v;
+    if (tail || dc)
+    {
+      // The reference's CTF table is not Hermitian along kx (quirk Q1), so neither is V in
+      // the two self-conjugate columns ky = 0 and ky = N/2.  A c2r transform (FFTW) only sees
+      // the Hermitian part of these columns: Re of their kx-transform.  Store that part,
+      // V_sym[kx] = (V[kx] + conj V[-kx]) / 2, so that the fused kernel can pack the two
+      // columns into one complex transform.  sumC / sumsquareC use the unsymmetrised V.
+      const int t = tail ? i - L::MAIN4 : i / L::KC; // = n1p * R2 + n2
+      const int n2 = t % L::R2, n1p = t / L::R2;
+      float pv[4];
+#pragma unroll
+      for (int e = 0; e < 2; e++)
+      {
+        const int kx = (2 * n1p + e) * L::R2 + n2;
+        const int kxp = (N - kx) % N;
+        const int m1 = kxp / L::R2, m2 = kxp % L::R2;
+        const int ip = tail ? L::MAIN4 + (m1 / 2) * L::R2 + m2 : L::main_idx(0, m1 / 2, m2, 0);
+        const float4 ap = P[ip], kp = K[ip];
+        if (m1 & 1)
+        {
+          pv[2 * e] = ap.z * kp.z + ap.w * kp.w;
+          pv[2 * e + 1] = ap.w * kp.z - ap.z * kp.w;
+        }
+        else
+        {
+          pv[2 * e] = ap.x * kp.x + ap.y * kp.y;
+          pv[2 * e + 1] = ap.y * kp.x - ap.x * kp.y;
+        }
+      }
+      vs.x = 0.5f * (v.x + pv[0]);
+      vs.y = 0.5f * (v.y - pv[1]);
+      vs.z = 0.5f * (v.z + pv[2]);
+      vs.w = 0.5f * (v.w - pv[3]);
+    }
+    V[i] = vs;
     acc += w * (v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w);
     if (i == 0)
       sumC = v.x; // kx = 0, ky = 0

@@ -176,26 +176,32 @@ def quat_to_rot(q: np.ndarray) -> np.ndarray:
 
 
 def project_numpy(model: np.ndarray, q: np.ndarray, n: int, px: float) -> np.ndarray:
-    """Small stand-alone projector for making particles (sphere footprints)."""
+    """Small stand-alone projector for making particles (sphere footprints, vectorised)."""
     rot = quat_to_rot(q)
     p = model[:, :3] @ rot.T
     img = np.zeros((n, n), dtype=np.float64)
     ci = np.floor(p[:, 0] / px + n / 2.0 + 0.5).astype(int)
     cj = np.floor(p[:, 1] / px + n / 2.0 + 0.5).astype(int)
-    for a in range(model.shape[0]):
-        r = model[a, 3]
-        d = model[a, 4]
-        if r <= px:
-            if 0 <= ci[a] < n and 0 <= cj[a] < n:
-                img[ci[a], cj[a]] += d
-            continue
-        ir = int(r / px) + 1
-        if ci[a] < ir or cj[a] < ir or ci[a] >= n - ir or cj[a] >= n - ir:
-            continue
-        o = np.arange(-ir, ir + 1)
-        dist = (o[:, None] ** 2 + o[None, :] ** 2) * px * px
-        w = np.where(dist < r * r, 2.0 * np.sqrt(np.maximum(r * r - dist, 0.0)), 0.0)
-        img[ci[a] - ir:ci[a] + ir + 1, cj[a] - ir:cj[a] + ir + 1] += w * d * 3.0 / (4 * np.pi * r ** 3) * px * px
+    r = model[:, 3]
+    d = model[:, 4]
+    small = r <= px
+    ok = small & (ci >= 0) & (ci < n) & (cj >= 0) & (cj < n)
+    np.add.at(img, (ci[ok], cj[ok]), d[ok])
+    ir = (r / px).astype(int) + 1
+    big = (~small) & (ci >= ir) & (cj >= ir) & (ci < n - ir) & (cj < n - ir)
+    if big.any():
+        irmax = int(ir[big].max())
+        o = np.arange(-irmax, irmax + 1)
+        di, dj = np.meshgrid(o, o, indexing="ij")
+        di = di.ravel()[None, :]
+        dj = dj.ravel()[None, :]
+        rb, db, cib, cjb, irb = r[big, None], d[big, None], ci[big, None], cj[big, None], ir[big, None]
+        dist = (di * di + dj * dj) * px * px
+        inside = (dist < rb * rb) & (np.abs(di) <= irb) & (np.abs(dj) <= irb)
+        w = 2.0 * np.sqrt(np.maximum(rb * rb - dist, 0.0)) * db * 3.0 / (4 * np.pi * rb ** 3) * px * px
+        ii = np.broadcast_to(cib + di, w.shape)[inside]
+        jj = np.broadcast_to(cjb + dj, w.shape)[inside]
+        np.add.at(img, (ii, jj), w[inside])
     return img
 
 

