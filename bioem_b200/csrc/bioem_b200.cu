@@ -146,8 +146,8 @@ static cudaError_t launch_fft2d(const float *imgs, const double *tempden, int nb
   using L = Lay<N>;
   dim3 g1((N / 2 + L::PC - 1) / L::PC, nimg);
   fft_rows_kernel<N><<<g1, NT, 0, s>>>(imgs, tempden, nbands, normDen, tw_fwd, scratch);
-  dim3 g2(L::NCH + 1, nimg);
-  const size_t smem2 = sizeof(float2) * (size_t) (L::KC * N + N);
+  dim3 g2((N / 2 + 1 + L::FKC - 1) / L::FKC, nimg);
+  const size_t smem2 = sizeof(float2) * (size_t) (L::FKC * N + N);
   cudaError_t e = cudaFuncSetAttribute(fft_cols_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem2);
   if (e != cudaSuccess)
     return e;
@@ -160,16 +160,6 @@ static cudaError_t launch_conv(const float4 *proj, const float4 *ctf, const doub
 {
   dim3 g(C, OBcur);
   ctf_conv_kernel<N><<<g, NT, 0, s>>>(proj, ctf, prior, conv, cpar, C, Nt);
-  return cudaGetLastError();
-}
-template <int N> static cudaError_t launch_lik(const LikParams &p, int nblocks, cudaStream_t s)
-{
-  const size_t smem = lik_smem_bytes<N>(p.nw);
-  // per device context, so set it on every launch (cheap next to the kernel)
-  cudaError_t e = cudaFuncSetAttribute(likelihood_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-  if (e != cudaSuccess)
-    return e;
-  likelihood_kernel<N><<<nblocks, NT, smem, s>>>(p);
   return cudaGetLastError();
 }
 template <int N> static size_t lik_smem(int nw) { return lik_smem_bytes<N>(nw); }
@@ -224,13 +214,17 @@ static cudaError_t do_conv(int N, const float4 *proj, const float4 *ctf, const d
   }
   return cudaErrorInvalidValue;
 }
-static cudaError_t do_lik(int N, const LikParams &p, int nblocks, cudaStream_t s)
+// the fused kernel's variants live in one translation unit per image edge (lik_instance.inl)
+#define X(n) extern "C" cudaError_t bioem_lik_launch_##n(const bioem::LikParams *, int, int, cudaStream_t);
+BIOEM_SIZES(X)
+#undef X
+static cudaError_t do_lik(int N, const LikParams &p, int nblocks, int maxD, cudaStream_t s)
 {
   switch (N)
   {
 #define X(n)                                                                                              \
   case n:                                                                                                 \
-    return launch_lik<n>(p, nblocks, s);
+    return bioem_lik_launch_##n(&p, nblocks, maxD, s);
     BIOEM_SIZES(X)
 #undef X
   }
@@ -693,7 +687,7 @@ int bioem_b200_run(bioem_b200_handle h, int oBegin, int oEnd)
       CU(cudaEventCreate(&e1));
       CU(cudaEventRecord(e0, h->stream));
     }
-    CU(do_lik(h->N, lp, h->M * NG, h->stream));
+    CU(do_lik(h->N, lp, h->M * NG, h->cfg.maxDisplaceCenter, h->stream));
     if (h->time_kernels)
     {
       CU(cudaEventRecord(e1, h->stream));
@@ -881,7 +875,7 @@ int bioem_b200_debug_correlation(bioem_b200_handle h, int o, int c, int m, float
   lp.dbg_values = d_dbg;
   lp.M = 1;
   lp.OG = 1;
-  CU(do_lik(h->N, lp, 1, h->stream));
+  CU(do_lik(h->N, lp, 1, h->cfg.maxDisplaceCenter, h->stream));
   CU(cudaMemcpyAsync(values, d_dbg + (size_t) c * nv, sizeof(float) * nv, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   cudaFree(d_dbg);

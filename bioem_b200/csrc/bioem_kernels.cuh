@@ -26,11 +26,24 @@ namespace bioem
 
 constexpr int NT = 256; // threads per CTA for the FFT kernels
 
+constexpr int largest_divisor_leq(int n, int lim)
+{
+  int best = 1;
+  for (int d = 1; d <= lim; d++)
+    if (n % d == 0)
+      best = d;
+  return best;
+}
+
 template <int N> struct Lay
 {
   using G = bfft::Geo<N>;
-  static constexpr int R1 = G::R1, R2 = G::R2, KC = G::KC, PC = G::PC;
+  static constexpr int R1 = G::R1, R2 = G::R2, PC = G::PC;
   static constexpr int NCOL = N / 2;
+  // columns per chunk of the packed layout = columns one warp transforms at a time in the
+  // fused kernel (lanes = R2 sub-sequences x KC columns)
+  static constexpr int KC = largest_divisor_leq(NCOL, (32 / R2) > 0 ? (32 / R2) : 1);
+  static constexpr int FKC = G::KC; // columns per CTA chunk of the forward column-FFT kernel
   static constexpr int NCH = NCOL / KC;
   static constexpr int MAIN4 = NCOL * N / 2;
   static constexpr int TAIL4 = N / 2;
@@ -183,6 +196,7 @@ struct ProjParams
   float pixelSize;
 };
 
+#ifndef BIOEM_LIK_ONLY // non-template kernels: defined once, in bioem_b200.cu
 __global__ void __launch_bounds__(256) project_kernel(ProjParams p)
 {
   extern __shared__ float band[]; // band_rows * N
@@ -305,6 +319,8 @@ __global__ void __launch_bounds__(256) project_kernel(ProjParams p)
   }
 }
 
+#endif // BIOEM_LIK_ONLY
+
 // ===========================================================================
 // stage 1b: forward 2-D r2c FFT of real images -> packed half-spectrum.
 // rows pass (two real rows per complex transform) to a row-major scratch
@@ -401,15 +417,14 @@ __global__ void __launch_bounds__(NT) fft_cols_kernel(const float2 *__restrict__
                                                       float4 *__restrict__ packed)
 {
   using L = Lay<N>;
-  constexpr int R1 = L::R1, R2 = L::R2, KC = L::KC;
+  constexpr int R1 = L::R1, R2 = L::R2, KC = L::FKC;
   constexpr int NC1 = N / 2 + 1;
   extern __shared__ __align__(16) unsigned char smem_cols[];
   float2 *E = reinterpret_cast<float2 *>(smem_cols); // [KC * N]
   float2 *TW = E + KC * N;                           // [N]
   const int tid = threadIdx.x;
   const int img = blockIdx.y;
-  const int ch = blockIdx.x; // NCH chunks + one extra for the Nyquist column
-  const int ky0 = ch * KC;
+  const int ky0 = blockIdx.x * KC; // chunks cover ky = 0 .. N/2 (the last one may be partial)
   const int ncol = min(KC, NC1 - ky0);
   for (int i = tid; i < N; i += NT)
     TW[i] = tw_fwd[i];
@@ -445,14 +460,15 @@ __global__ void __launch_bounds__(NT) fft_cols_kernel(const float2 *__restrict__
       for (int n2 = 0; n2 < R2; n2++)
         y[n2] = E[(k1 * R2 + n2) * KC + kyl];
       bfft::Dft<R2, -1>::run(y);
+      const int ky = ky0 + kyl;
 #pragma unroll
       for (int k2 = 0; k2 < R2; k2++)
       {
         const int kx = k1 + R1 * k2;
         const int n1 = kx / R2, m2 = kx % R2;
         size_t f4;
-        if (ch < L::NCH)
-          f4 = (size_t) L::main_idx(ch, n1 / 2, m2, kyl);
+        if (ky < L::NCOL)
+          f4 = (size_t) L::main_idx(ky / L::KC, n1 / 2, m2, ky % L::KC);
         else
           f4 = (size_t) L::MAIN4 + (n1 / 2) * R2 + m2;
         dst2[f4 * 2 + (n1 & 1)] = y[k2];
@@ -461,6 +477,7 @@ __global__ void __launch_bounds__(NT) fft_cols_kernel(const float2 *__restrict__
   }
 }
 
+#ifndef BIOEM_LIK_ONLY // non-template kernels: defined once, in bioem_b200.cu
 // per-image sum and sum of squares, strictly sequential float accumulation in
 // row-major order like the reference (bioem.cpp:2087-2107); one-off input prep.
 __global__ void image_sums_kernel(const float *__restrict__ imgs, int n2, int M, float *__restrict__ sum,
@@ -480,6 +497,8 @@ __global__ void image_sums_kernel(const float *__restrict__ imgs, int n2, int M,
   sum[m] = s;
   sumsq[m] = ss;
 }
+
+#endif // BIOEM_LIK_ONLY
 
 // ===========================================================================
 // stage 2: V = P * conj(K_c) on packed maps, sumC, sumsquareC, and the
@@ -572,21 +591,6 @@ __global__ void __launch_bounds__(NT) ctf_conv_kernel(const float4 *__restrict__
   }
 }
 
-// ===========================================================================
-// stages 3-5 fused.  One CTA owns one particle image m and a group of
-// orientations of the current batch; for every (orientation, CTF) pair it
-//   * streams the conv spectrum (L2) and the particle spectrum (L2/HBM) with
-//     coalesced 128-bit loads, multiplies conv * conj(particle) in registers,
-//   * runs the column pass of the inverse 2-D FFT keeping only the displacement
-//     window rows (output pruning) in shared memory,
-//   * runs the row pass two real rows at a time, in place,
-//   * evaluates the analytic log-posterior's displacement-dependent factor
-//     (firstele, FP32, reference operation order) straight out of the FFT
-//     registers, and reduces (min firstele <=> max logpro, sum of exp) in the CTA,
-//   * folds the result into the image's running (Constoadd, Total, arg-max)
-//     kept in registers of the bookkeeping thread.
-// No correlation map ever leaves the SM.
-// ===========================================================================
 struct LikParams
 {
   const float4 *convs; // [OBcur*C][MAP4]
@@ -609,16 +613,34 @@ struct LikParams
   float tcut; // relative firstele excess beyond which exp() underflows to nothing
 };
 
-template <int N> __host__ __device__ constexpr size_t lik_smem_bytes(int nw)
+// Shared-memory plan of the fused kernel.
+//   Y   [nwp][YS]  window rows of the column-transformed spectrum (float2); YS = NCOL + pad so
+//                  that consecutive rows fall into different banks
+//   E   per warp [R1][ES] exchange buffer of the column pass (float2); aliased by FE [nw*nw]
+//   TW  [N] twiddles, WT [N] window table
+template <int N> struct LikSmem
 {
   using L = Lay<N>;
-  const int nwp = nw + (nw & 1);
-  size_t e_words = (size_t) L::KC * N * 2; // floats
-  size_t fe_words = (size_t) nw * nw;
-  size_t ex = e_words > fe_words ? e_words : fe_words;
-  ex = (ex + 3) & ~(size_t) 3;
-  return ((size_t) nwp * L::NCOL * 2 + ex + (size_t) N * 2) * sizeof(float) + ((N + 15) & ~15);
-}
+  static constexpr int NWARP = NT / 32;
+  static constexpr int KC = L::KC;
+  // pass-2 lanes are (k1, kyl): address k1*ES + kyl -> distinct bank pairs in a half warp
+  static constexpr int ES = L::R2 * KC + ((KC - L::R2 * KC) % 16 + 16) % 16;
+  static constexpr int YS = L::NCOL + ((KC - L::NCOL) % 16 + 16) % 16 + (N - 2 * (L::NCOL + ((KC - L::NCOL) % 16 + 16) % 16) > 0 ? 16 : 0);
+  static_assert(2 * YS >= N, "a row pair must hold one N-point transform in place");
+  static constexpr int EW = L::R1 * ES; // float2 per warp
+  __host__ __device__ static constexpr size_t ex_floats(int nw)
+  {
+    size_t e = (size_t) NWARP * EW * 2, f = (size_t) nw * nw;
+    size_t x = e > f ? e : f;
+    return (x + 3) & ~(size_t) 3;
+  }
+  __host__ __device__ static constexpr size_t bytes(int nw)
+  {
+    const int nwp = nw + (nw & 1);
+    return ((size_t) nwp * YS * 2 + ex_floats(nw) + (size_t) N * 2) * sizeof(float) + ((N + 15) & ~15);
+  }
+};
+template <int N> __host__ __device__ constexpr size_t lik_smem_bytes(int nw) { return LikSmem<N>::bytes(nw); }
 
 __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int m)
 {
@@ -628,24 +650,49 @@ __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v,
   return ((unsigned long long) hi << 32) | lo;
 }
 
-template <int N> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)) likelihood_kernel(LikParams p)
+// ===========================================================================
+// stages 3-5 fused.  One CTA owns one particle image m and a group of
+// orientations of the current batch; for every (orientation, CTF) pair it
+//   * streams the conv spectrum (L2) and the particle spectrum (L2/HBM) with fully
+//     coalesced 128-bit loads (one 512-byte line per warp instruction) and multiplies
+//     conv * conj(particle) in registers,
+//   * column pass of the inverse 2-D FFT, WARP-SYNCHRONOUS: each warp owns KC columns at a
+//     time (lanes = R2 sub-sequences x KC columns), radix-R1 in registers, twiddle, exchange
+//     through the warp's private shared-memory tile (only __syncwarp), radix-R2 in registers;
+//     only the displacement-window rows are kept (output pruning),
+//   * row pass, also warp-synchronous: two real rows per complex transform, in place,
+//   * the displacement-dependent factor of the analytic log-posterior (firstele, FP32,
+//     reference operation order) straight out of the FFT registers; (min firstele <=> max
+//     logpro, sum of exp) reduced in the CTA,
+//   * the image's running (Constoadd, Total, arg-max) kept in registers of one thread.
+// Three CTA-wide barriers per likelihood; no correlation map ever leaves the SM.
+// ===========================================================================
+// W = number of leading and of trailing radix-R2 output groups k2 that can hold window
+// displacements (k2 < W or k2 >= R2 - W); outputs of the other groups are never formed
+// (the compiler prunes the butterflies that only feed them).  2W >= R2 keeps everything.
+template <int N, int W> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)) likelihood_kernel(LikParams p)
 {
   using L = Lay<N>;
-  constexpr int R1 = L::R1, R2 = L::R2, KC = L::KC, PC = L::PC, NCOL = L::NCOL, NCH = L::NCH;
+  using SM = LikSmem<N>;
+  constexpr int NK = (2 * W >= L::R2) ? L::R2 : 2 * W; // output groups kept
+  constexpr int NKW = (NK + 3) / 4;                    // 32-bit words of a per-lane byte table
+  constexpr int R1 = L::R1, R2 = L::R2, KC = L::KC, NCOL = L::NCOL, NCH = L::NCH;
+  constexpr int ES = SM::ES, YS = SM::YS, NWARP = SM::NWARP;
+  constexpr int PW = KC;             // row pairs per warp task (lanes = PW x R2)
+  constexpr int P2 = (KC * R1 + 31) / 32; // pass-2 trips
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nw = p.nw, nwp = p.nwp;
-  float2 *Y = reinterpret_cast<float2 *>(smem_raw); // [nwp][NCOL]
-  float2 *E = Y + (size_t) nwp * NCOL;             // [KC*N], aliased by FE
-  float *FE = reinterpret_cast<float *>(E);
-  size_t ex = (size_t) KC * N * 2 > (size_t) nw * nw ? (size_t) KC * N * 2 : (size_t) nw * nw;
-  ex = (ex + 3) & ~(size_t) 3;
-  float2 *TW = reinterpret_cast<float2 *>(FE + ex);
+  float2 *Y = reinterpret_cast<float2 *>(smem_raw); // [nwp][YS]
+  float2 *Eall = Y + (size_t) nwp * YS;
+  float *FE = reinterpret_cast<float *>(Eall);
+  float2 *TW = reinterpret_cast<float2 *>(FE + SM::ex_floats(nw));
   unsigned char *WT = reinterpret_cast<unsigned char *>(TW + N);
   __shared__ unsigned long long s_key[2];
-  __shared__ float s_wsum[2][NT / 32];
+  __shared__ float s_wsum[2][NWARP];
   __shared__ float s_winv[2];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float2 *E = Eall + (size_t) warp * SM::EW;
   const int m = blockIdx.x % p.M;
   const int g = blockIdx.x / p.M;
   const int o_lo = g * p.OG;
@@ -658,6 +705,38 @@ template <int N> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)) likel
   }
   if (tid < 2)
     s_key[tid] = ~0ull;
+  __syncthreads();
+
+  // lane roles (fixed for the whole kernel)
+  const int c1_n2 = lane / KC, c1_ky = lane % KC; // column pass 1: (sub-sequence, column)
+  const bool c1_act = lane < R2 * KC;
+  const int r1_pl = lane / R2, r1_n2 = lane % R2; // row pass 1: (pair, sub-sequence)
+  const bool r1_act = lane < PW * R2;
+  // per-lane tables: window index (byte, 255 = not a window displacement) of raw index
+  // k1 + R1*k2 for the kept k2, for this lane's k1 in the column role and in the row role
+  unsigned ctab[P2][NKW], rtab[P2][NKW];
+#pragma unroll
+  for (int t = 0; t < P2; t++)
+  {
+    const int item = lane + 32 * t;
+    const bool act = item < KC * R1;
+    const int kc = item / KC; // column pass 2: item = k1*KC + kyl
+    const int kr = item % R1; // row pass 2:    item = pl*R1 + k1
+#pragma unroll
+    for (int w = 0; w < NKW; w++)
+    {
+      ctab[t][w] = 0xffffffffu;
+      rtab[t][w] = 0xffffffffu;
+    }
+    bfft::static_for<0, NK>([&](auto j_) {
+      constexpr int j = decltype(j_)::value;
+      constexpr int k2 = (NK == R2) ? j : (j < W ? j : R2 - NK + j);
+      const unsigned bc = act ? WT[kc + R1 * k2] : 255u;
+      const unsigned br = act ? WT[kr + R1 * k2] : 255u;
+      ctab[t][j / 4] = (ctab[t][j / 4] & ~(0xffu << (8 * (j % 4)))) | (bc << (8 * (j % 4)));
+      rtab[t][j / 4] = (rtab[t][j / 4] & ~(0xffu << (8 * (j % 4)))) | (br << (8 * (j % 4)));
+    });
+  }
 
   const float4 *ref = p.refs + (size_t) m * L::MAP4;
   const float sR = p.sumRef[m], ssR = p.sumsqRef[m];
@@ -668,9 +747,7 @@ template <int N> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)) likel
   float bk_lpf = 0.f, bk_v = 0.f, bk_sC = 0.f, bk_ssC = 0.f;
   int bk_o = 0, bk_c = 0, bk_lin = 0;
   double an_Const = kMinProb, an_Total = 0.0;
-
   int buf = 0;
-  __syncthreads();
 
   for (int ol = o_lo; ol < o_hi; ol++)
   {
@@ -687,18 +764,13 @@ template <int N> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)) likel
       const float f_c = __fmul_rn(__fmul_rn(ssR, cp.sumC), cp.sumC);
       const float f_d = __fmul_rn(__fmul_rn(sR, sR), cp.sumsqC);
 
-      if (nw & 1) // zero the padding row of the last row pair
-        for (int i = tid; i < NCOL; i += NT)
-          Y[(size_t) nw * NCOL + i] = make_float2(0.f, 0.f);
-
-      // ------------------------------------------------ column pass (along kx)
-      for (int ch = 0; ch < NCH; ch++)
+      // ------------------------------------------------ column pass (along kx), per warp
+      for (int ch = warp; ch < NCH; ch += NWARP)
       {
-        for (int item = tid; item < R2 * KC; item += NT)
+        if (c1_act)
         {
-          const int n2 = item / KC, kyl = item % KC;
           float2 x[R1];
-          const int base = L::main_idx(ch, 0, n2, kyl);
+          const int base = ch * (R1 / 2) * R2 * KC + lane; // == main_idx(ch, 0, c1_n2, c1_ky)
 #pragma unroll
           for (int n1p = 0; n1p < R1 / 2; n1p++)
           {
@@ -707,14 +779,14 @@ template <int N> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)) likel
             x[2 * n1p] = bfft::cmulc(make_float2(v.x, v.y), make_float2(r.x, r.y));
             x[2 * n1p + 1] = bfft::cmulc(make_float2(v.z, v.w), make_float2(r.z, r.w));
           }
-          if (ch == 0 && kyl == 0)
+          if (ch == 0 && c1_ky == 0)
           {
             // pack the Nyquist column into the (Hermitian) DC column: Z = X0 + i*X_{N/2}
 #pragma unroll
             for (int n1p = 0; n1p < R1 / 2; n1p++)
             {
-              const float4 r = ldg4(ref + L::MAIN4 + n1p * R2 + n2);
-              const float4 v = ldg4(conv + L::MAIN4 + n1p * R2 + n2);
+              const float4 r = ldg4(ref + L::MAIN4 + n1p * R2 + c1_n2);
+              const float4 v = ldg4(conv + L::MAIN4 + n1p * R2 + c1_n2);
               const float2 t0 = bfft::cmulc(make_float2(v.x, v.y), make_float2(r.x, r.y));
               const float2 t1 = bfft::cmulc(make_float2(v.z, v.w), make_float2(r.z, r.w));
               x[2 * n1p].x -= t0.y;
@@ -726,45 +798,59 @@ template <int N> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)) likel
           bfft::Dft<R1, 1>::run(x);
 #pragma unroll
           for (int k1 = 1; k1 < R1; k1++)
-            x[k1] = bfft::cmul(x[k1], TW[n2 * R1 + k1]);
+            x[k1] = bfft::cmul(x[k1], TW[c1_n2 * R1 + k1]);
 #pragma unroll
           for (int k1 = 0; k1 < R1; k1++)
-            E[(k1 * R2 + n2) * KC + kyl] = x[k1];
+            E[k1 * ES + lane] = x[k1];
         }
-        __syncthreads();
-        for (int item = tid; item < R1 * KC; item += NT)
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < P2; t++)
         {
-          const int k1 = item / KC, kyl = item % KC;
-          float2 y[R2];
-#pragma unroll
-          for (int n2 = 0; n2 < R2; n2++)
-            y[n2] = E[(k1 * R2 + n2) * KC + kyl];
-          bfft::Dft<R2, 1>::run(y);
-#pragma unroll
-          for (int k2 = 0; k2 < R2; k2++)
+          const int item = lane + 32 * t;
+          if (item < KC * R1)
           {
-            const int w = WT[k1 + R1 * k2];
-            if (w != 255)
-              Y[(size_t) w * NCOL + ch * KC + kyl] = y[k2];
+            const int k1 = item / KC, kyl = item % KC;
+            float2 y[R2];
+#pragma unroll
+            for (int n2 = 0; n2 < R2; n2++)
+              y[n2] = E[k1 * ES + n2 * KC + kyl];
+            bfft::Dft<R2, 1>::run(y);
+            float2 *Ycol = Y + ch * KC + kyl;
+            bfft::static_for<0, NK>([&](auto j_) {
+              constexpr int j = decltype(j_)::value;
+              constexpr int k2 = (NK == R2) ? j : (j < W ? j : R2 - NK + j);
+              const unsigned w = (ctab[t][j / 4] >> (8 * (j % 4))) & 0xffu;
+              if (w != 255u)
+                Ycol[w * YS] = y[k2];
+            });
           }
         }
-        __syncthreads();
+        __syncwarp();
       }
+      __syncthreads(); // window rows of all columns are in Y
 
       // ------------------------------------------------ row pass (along ky), 2 rows per transform
       unsigned long long best = ~0ull;
       float best_v = 0.f;
       const int npairs = nwp / 2;
-      for (int p0 = 0; p0 < npairs; p0 += PC)
+      for (int p0 = warp * PW; p0 < npairs; p0 += NWARP * PW)
       {
-        const int npl = min(PC, npairs - p0);
+        const int npl = min(PW, npairs - p0);
+        if ((nw & 1) && p0 + npl == npairs)
+        {
+          // zero the padding row of the last pair (it holds leftovers of the previous transform)
+          for (int i = lane; i < NCOL; i += 32)
+            Y[(size_t) nw * YS + i] = make_float2(0.f, 0.f);
+          __syncwarp();
+        }
         float2 x[R1];
-        const int pl1 = tid / R2, n2 = tid % R2;
-        const bool act1 = pl1 < npl;
-        float2 *Yp = Y + (size_t) (2 * (p0 + pl1)) * NCOL; // rows a,b contiguous: N complex
+        const bool act1 = r1_act && r1_pl < npl;
+        float2 *Yp = Y + (size_t) (2 * (p0 + r1_pl)) * YS; // rows a, b; the pair region holds N points
         if (act1)
         {
-          const float2 *Ya = Yp, *Yb = Yp + NCOL;
+          const float2 *Ya = Yp, *Yb = Yp + YS;
+          const int n2 = r1_n2;
 #pragma unroll
           for (int n1 = 0; n1 < R1; n1++)
           {
@@ -797,61 +883,69 @@ template <int N> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)) likel
           for (int k1 = 1; k1 < R1; k1++)
             x[k1] = bfft::cmul(x[k1], TW[n2 * R1 + k1]);
         }
-        __syncthreads(); // all reads of this chunk's rows are done: safe to overwrite in place
+        __syncwarp(); // all reads of this task's rows are done: overwrite in place
         if (act1)
         {
 #pragma unroll
           for (int k1 = 0; k1 < R1; k1++)
-            Yp[k1 * R2 + ((n2 + k1) % R2)] = x[k1];
+            Yp[k1 * R2 + ((r1_n2 + k1) % R2)] = x[k1];
         }
-        __syncthreads();
-        for (int item = tid; item < npl * R1; item += NT)
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < P2; t++)
         {
+          const int item = lane + 32 * t;
           const int pl = item / R1, k1 = item % R1;
-          const float2 *Yq = Y + (size_t) (2 * (p0 + pl)) * NCOL;
-          float2 y[R2];
-#pragma unroll
-          for (int n2b = 0; n2b < R2; n2b++)
-            y[n2b] = Yq[k1 * R2 + ((n2b + k1) % R2)];
-          bfft::Dft<R2, 1>::run(y);
-          const int wa = 2 * (p0 + pl), wb = wa + 1;
-          const bool vb = wb < nw;
-#pragma unroll
-          for (int k2 = 0; k2 < R2; k2++)
+          if (item < KC * R1 && pl < npl)
           {
-            const int wy = WT[k1 + R1 * k2];
-            if (wy != 255)
-            {
+            const float2 *Yq = Y + (size_t) (2 * (p0 + pl)) * YS;
+            float2 y[R2];
+#pragma unroll
+            for (int n2b = 0; n2b < R2; n2b++)
+              y[n2b] = Yq[k1 * R2 + ((n2b + k1) % R2)];
+            bfft::Dft<R2, 1>::run(y);
+            const int wa = 2 * (p0 + pl), wb = wa + 1;
+            const bool vb = wb < nw;
+            bfft::static_for<0, NK>([&](auto j_) {
+              constexpr int j = decltype(j_)::value;
+              constexpr int k2 = (NK == R2) ? j : (j < W ? j : R2 - NK + j);
+              const unsigned wy = (rtab[t][j / 4] >> (8 * (j % 4))) & 0xffu;
+              const bool in = wy != 255u;
               {
                 const float v = y[k2].x * p.invNN;
                 const float fe = __fsub_rn(__fsub_rn(__fadd_rn(__fmul_rn(Nt, __fsub_rn(f_a, __fmul_rn(v, v))), __fmul_rn(f_b, v)), f_c), f_d);
-                const int lin = wa * nw + wy;
-                FE[lin] = fe;
+                const int lin = wa * nw + (int) wy;
                 const unsigned long long key = ((unsigned long long) __float_as_uint(fe) << 32) | (unsigned) lin;
-                if (key < best)
+                if (in)
                 {
-                  best = key;
-                  best_v = v;
+                  FE[lin] = fe;
+                  if (key < best)
+                  {
+                    best = key;
+                    best_v = v;
+                  }
+                  if (p.dbg_values)
+                    p.dbg_values[((size_t) oc * p.M + m) * nw * nw + lin] = v;
                 }
-                if (p.dbg_values)
-                  p.dbg_values[((size_t) oc * p.M + m) * nw * nw + lin] = v;
               }
-              if (vb)
               {
                 const float v = y[k2].y * p.invNN;
                 const float fe = __fsub_rn(__fsub_rn(__fadd_rn(__fmul_rn(Nt, __fsub_rn(f_a, __fmul_rn(v, v))), __fmul_rn(f_b, v)), f_c), f_d);
-                const int lin = wb * nw + wy;
-                FE[lin] = fe;
+                const int lin = wb * nw + (int) wy;
                 const unsigned long long key = ((unsigned long long) __float_as_uint(fe) << 32) | (unsigned) lin;
-                if (key < best)
+                if (in && vb)
                 {
-                  best = key;
-                  best_v = v;
+                  FE[lin] = fe;
+                  if (key < best)
+                  {
+                    best = key;
+                    best_v = v;
+                  }
+                  if (p.dbg_values)
+                    p.dbg_values[((size_t) oc * p.M + m) * nw * nw + lin] = v;
                 }
-                if (p.dbg_values)
-                  p.dbg_values[((size_t) oc * p.M + m) * nw * nw + lin] = v;
               }
-            }
+            });
           }
         }
       }
@@ -866,7 +960,7 @@ template <int N> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)) likel
       }
       if (lane == 0)
         atomicMin(&s_key[buf], wbest);
-      __syncthreads();
+      __syncthreads(); // FE complete, minimum known
       const unsigned long long kmin = s_key[buf];
       const float fmin = __uint_as_float((unsigned) (kmin >> 32));
       if (best == kmin)
@@ -888,7 +982,7 @@ template <int N> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)) likel
         S += __shfl_xor_sync(0xffffffffu, S, s);
       if (lane == 0)
         s_wsum[buf][warp] = S;
-      __syncthreads();
+      __syncthreads(); // FE consumed (E may be overwritten), partial sums visible
 
       // ------------------------------------------------ bookkeeping (bioem_algorithm.h:84-141)
       if (tid == 0)
@@ -896,7 +990,7 @@ template <int N> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)) likel
         s_key[buf ^ 1] = ~0ull;
         float Ssum = 0.f;
 #pragma unroll
-        for (int w = 0; w < NT / 32; w++)
+        for (int w = 0; w < NWARP; w++)
           Ssum += s_wsum[buf][w];
         const double lp = p.acoef_d * log((double) fmin) + cp.Bterm;
         const float lpf = (float) lp;
@@ -952,6 +1046,7 @@ template <int N> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)) likel
   }
 }
 
+#ifndef BIOEM_LIK_ONLY
 // fold the per-group partials of one batch into the running per-image state, in
 // orientation order (strict '<' keeps the first maximum, bioem_algorithm.h:96)
 __global__ void merge_partials_kernel(const Running *__restrict__ partials, int NG, int M, Running *__restrict__ state)
@@ -1039,5 +1134,7 @@ __global__ void finalize_kernel(const Running *__restrict__ state, const float *
   }
   out[m] = o;
 }
+
+#endif // BIOEM_LIK_ONLY
 
 } // namespace bioem

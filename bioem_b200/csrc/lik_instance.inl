@@ -1,0 +1,42 @@
+// One translation unit per image edge (BIOEM_N), so the fused-kernel variants compile in
+// parallel.  Exports  bioem_lik_launch_<N>(params, nblocks, maxDisplaceCenter, stream).
+#define BIOEM_LIK_ONLY
+#include "bioem_kernels.cuh"
+
+namespace bioem
+{
+template <int W> static cudaError_t lik_launch_w(const LikParams &p, int nblocks, cudaStream_t s)
+{
+  const size_t smem = lik_smem_bytes<BIOEM_N>(p.nw);
+  // attribute is per device context: set on every launch (cheap next to the kernel)
+  cudaError_t e = cudaFuncSetAttribute(likelihood_kernel<BIOEM_N, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+  if (e != cudaSuccess)
+    return e;
+  likelihood_kernel<BIOEM_N, W><<<nblocks, NT, smem, s>>>(p);
+  return cudaGetLastError();
+}
+} // namespace bioem
+
+#define BIOEM_CAT2(a, b) a##b
+#define BIOEM_CAT(a, b) BIOEM_CAT2(a, b)
+
+extern "C" cudaError_t BIOEM_CAT(bioem_lik_launch_, BIOEM_N)(const bioem::LikParams *p, int nblocks, int maxD, cudaStream_t s)
+{
+  using L = bioem::Lay<BIOEM_N>;
+  constexpr int HALF = L::R2 / 2;
+  // radix-R2 output groups that can hold a displacement in [-maxD, maxD]:
+  // k2 <= maxD/R1 at the low end, k2 >= R2 - ceil(maxD/R1) at the high end
+  const int need = maxD / L::R1 + 1;
+  if (need <= 1 && HALF > 1)
+    return bioem::lik_launch_w<1>(*p, nblocks, s);
+  if constexpr (HALF > 2)
+    if (need <= 2)
+      return bioem::lik_launch_w<2>(*p, nblocks, s);
+  if constexpr (HALF > 3)
+    if (need <= 3)
+      return bioem::lik_launch_w<3>(*p, nblocks, s);
+  if constexpr (HALF > 4)
+    if (need <= 4)
+      return bioem::lik_launch_w<4>(*p, nblocks, s);
+  return bioem::lik_launch_w<HALF>(*p, nblocks, s);
+}
