@@ -99,20 +99,31 @@ template <int I, int E, class F> BFFT_HD __forceinline__ void static_for(F &&f)
   }
 }
 
-BFFT_HD __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-BFFT_HD __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-BFFT_HD __forceinline__ float2 cmul(float2 a, float2 b)
+// Complex arithmetic on float2 = (re, im) with the sm_100a packed FP32 instructions
+// (FADD2 / FMUL2 / FFMA2: two FP32 lanes per thread per issue slot).  ptxas folds the
+// swap / sign patterns below into operand modifiers (.LO_HI, .NP, scalar broadcast), so a
+// complex add is ONE instruction, a multiply by +-i is free, and a complex multiply is two.
+#define BFFT_D __device__ __forceinline__
+BFFT_D float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+BFFT_D float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+// a + i*b and a - i*b
+BFFT_D float2 cadd_i(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.y, b.x)); }
+BFFT_D float2 csub_i(float2 a, float2 b) { return __fadd2_rn(a, make_float2(b.y, -b.x)); }
+BFFT_D float2 cmul(float2 a, float2 b)
 {
-  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+  return __ffma2_rn(make_float2(-a.y, a.x), make_float2(b.y, b.y), __fmul2_rn(a, make_float2(b.x, b.x)));
 }
 // a * conj(b)
-BFFT_HD __forceinline__ float2 cmulc(float2 a, float2 b)
+BFFT_D float2 cmulc(float2 a, float2 b)
 {
-  return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+  return __ffma2_rn(make_float2(a.y, -a.x), make_float2(b.y, b.y), __fmul2_rn(a, make_float2(b.x, b.x)));
 }
+// a * s for a real scalar s, and r*s + a
+BFFT_D float2 cscale(float2 a, float s) { return __fmul2_rn(a, make_float2(s, s)); }
+BFFT_D float2 cfma_r(float s, float2 r, float2 a) { return __ffma2_rn(make_float2(s, s), r, a); }
 
 // multiply by the compile-time constant exp(SIGN * 2*pi*i * P / Q)
-template <int SIGN, int P, int Q> BFFT_HD __forceinline__ float2 cmul_root(float2 a)
+template <int SIGN, int P, int Q> BFFT_D float2 cmul_root(float2 a)
 {
   constexpr cs_t w = unit_root((long long) SIGN * P, Q);
   constexpr float c = (float) w.c, s = (float) w.s;
@@ -125,7 +136,7 @@ template <int SIGN, int P, int Q> BFFT_HD __forceinline__ float2 cmul_root(float
   else if constexpr (w.c == 0.0 && w.s == -1.0)
     return make_float2(a.y, -a.x);
   else
-    return make_float2(a.x * c - a.y * s, a.x * s + a.y * c);
+    return __ffma2_rn(make_float2(-a.y, a.x), make_float2(s, s), __fmul2_rn(a, make_float2(c, c)));
 }
 
 BFFT_HD constexpr int pick_factor(int r)
@@ -147,12 +158,12 @@ template <int R, int SIGN, int A = pick_factor(R)> struct Dft;
 
 template <int SIGN> struct Dft<1, SIGN, 1>
 {
-  BFFT_HD __forceinline__ static void run(float2 *) {}
+  BFFT_D static void run(float2 *) {}
 };
 
 template <int SIGN> struct Dft<2, SIGN, 2>
 {
-  BFFT_HD __forceinline__ static void run(float2 *v)
+  BFFT_D static void run(float2 *v)
   {
     float2 a = v[0], b = v[1];
     v[0] = cadd(a, b);
@@ -162,16 +173,22 @@ template <int SIGN> struct Dft<2, SIGN, 2>
 
 template <int SIGN> struct Dft<4, SIGN, 4>
 {
-  BFFT_HD __forceinline__ static void run(float2 *v)
+  BFFT_D static void run(float2 *v)
   {
     float2 t0 = cadd(v[0], v[2]), t1 = csub(v[0], v[2]);
     float2 t2 = cadd(v[1], v[3]), d = csub(v[1], v[3]);
-    // (SIGN*i) * d
-    float2 t3 = make_float2(-SIGN * d.y, SIGN * d.x);
     v[0] = cadd(t0, t2);
-    v[1] = cadd(t1, t3);
     v[2] = csub(t0, t2);
-    v[3] = csub(t1, t3);
+    if constexpr (SIGN > 0)
+    { // t1 +- i*d
+      v[1] = cadd_i(t1, d);
+      v[3] = csub_i(t1, d);
+    }
+    else
+    {
+      v[1] = csub_i(t1, d);
+      v[3] = cadd_i(t1, d);
+    }
   }
 };
 
@@ -179,7 +196,7 @@ template <int SIGN> struct Dft<4, SIGN, 4>
 template <int R, int SIGN> struct Dft<R, SIGN, R>
 {
   static_assert(R % 2 == 1 && R >= 3, "prime kernel expects an odd prime");
-  BFFT_HD __forceinline__ static void run(float2 *v)
+  BFFT_D static void run(float2 *v)
   {
     constexpr int H = (R - 1) / 2;
     float2 s[H + 1], d[H + 1];
@@ -195,19 +212,20 @@ template <int R, int SIGN> struct Dft<R, SIGN, R>
     static_for<1, H + 1>([&](auto j_) {
       constexpr int j = decltype(j_)::value;
       float2 m = x0;
-      float2 e = make_float2(0.f, 0.f);
+      float2 e;
       static_for<1, H + 1>([&](auto k_) {
         constexpr int k = decltype(k_)::value;
         constexpr cs_t w = unit_root((long long) j * k, R);
         constexpr float c = (float) w.c, sn = (float) (SIGN * w.s);
-        m.x = fmaf(c, s[k].x, m.x);
-        m.y = fmaf(c, s[k].y, m.y);
-        e.x = fmaf(sn, d[k].x, e.x);
-        e.y = fmaf(sn, d[k].y, e.y);
+        m = cfma_r(c, s[k], m);
+        if constexpr (k == 1)
+          e = cscale(d[k], sn);
+        else
+          e = cfma_r(sn, d[k], e);
       });
       // X_j = m + i*e ; X_{R-j} = m - i*e
-      v[j] = make_float2(m.x - e.y, m.y + e.x);
-      v[R - j] = make_float2(m.x + e.y, m.y - e.x);
+      v[j] = cadd_i(m, e);
+      v[R - j] = csub_i(m, e);
     });
   }
 };
@@ -218,7 +236,7 @@ template <int R, int SIGN> struct Dft<R, SIGN, R>
 template <int R, int SIGN, int A> struct Dft
 {
   static_assert(R % A == 0 && A > 1 && A < R, "bad factorisation");
-  BFFT_HD __forceinline__ static void run(float2 *v)
+  BFFT_D static void run(float2 *v)
   {
     constexpr int B = R / A;
     float2 t[R]; // t[k1*B + n2]
