@@ -162,7 +162,7 @@ static cudaError_t launch_conv(const float4 *proj, const float4 *ctf, const doub
   ctf_conv_kernel<N><<<g, NT, 0, s>>>(proj, ctf, prior, conv, cpar, C, Nt);
   return cudaGetLastError();
 }
-template <int N> static size_t lik_smem(int nw) { return lik_smem_bytes<N>(nw); }
+template <int N> static size_t lik_smem(int maxD) { return lik_smem_bytes<N>(maxD); }
 
 static cudaError_t do_pack(int N, const float2 *src, float4 *dst, int nmaps, cudaStream_t s)
 {
@@ -230,13 +230,13 @@ static cudaError_t do_lik(int N, const LikParams &p, int nblocks, int maxD, cuda
   }
   return cudaErrorInvalidValue;
 }
-static size_t smem_for(int N, int nw)
+static size_t smem_for(int N, int maxD)
 {
   switch (N)
   {
 #define X(n)                                                                                              \
   case n:                                                                                                 \
-    return lik_smem<n>(nw);
+    return lik_smem<n>(maxD);
     BIOEM_SIZES(X)
 #undef X
   }
@@ -283,7 +283,7 @@ int bioem_b200_create(const bioem_b200_config *cfg, int device, bioem_b200_handl
   CU(cudaSetDevice(device));
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, device));
-  if (smem_for(N, nw) > (size_t) prop.sharedMemPerBlockOptin)
+  if (smem_for(N, cfg->maxDisplaceCenter) > (size_t) prop.sharedMemPerBlockOptin)
     return fail(BIOEM_B200_ERR_INVALID, "displacement window does not fit in shared memory for this image size");
   bioem_b200_context *h = new bioem_b200_context;
   h->cfg = *cfg;
@@ -649,8 +649,7 @@ static void fill_lik_params(bioem_b200_context *h, LikParams &lp, int o0, int OB
   lp.Ntotpi = h->cfg.Ntotpi;
   lp.invNN = 1.0f / (float) (N * N);
   lp.acoef_d = (double) (3.f - h->cfg.Ntotpi) * 0.5;
-  lp.acoef_f = (float) lp.acoef_d;
-  lp.tcut = (float) (40.0 / fabs(lp.acoef_d));
+  lp.ex2coef = (float) (lp.acoef_d * 1.4426950408889634074);
 }
 
 int bioem_b200_run(bioem_b200_handle h, int oBegin, int oEnd)

@@ -12,9 +12,9 @@
 // half-spectrum A[kx][ky], kx < N, ky <= N/2.  With N = R1*R2 (bfft::Geo<N>),
 // NCOL = N/2 and KC columns per chunk, element (kx = n1*R2 + n2, ky = ch*KC + kyl)
 // with ky < NCOL lives in float4 number
-//      ((ch*(R1/2) + n1/2)*R2 + n2)*KC + kyl ,   .xy if n1 even, .zw if n1 odd,
+//      ((ch*(R1/2) + n1/2)*KC + kyl)*R2 + n2 ,   .xy if n1 even, .zw if n1 odd,
 // i.e. exactly the order in which the column pass of the fused kernel reads it
-// (one fully coalesced LDG.128 per thread per two points).  The Nyquist column
+// (lane = kyl*R2 + n2: one fully coalesced LDG.128 per thread per two points).  The Nyquist column
 // ky = N/2 is a tail of N/2 float4: tail[(n1/2)*R2 + n2].
 #pragma once
 #include "fft_regs.cuh"
@@ -51,7 +51,27 @@ template <int N> struct Lay
   static_assert(PC * R2 <= NT && PC * R1 <= NT, "row-pass chunk must fit one item per thread");
   __host__ __device__ static constexpr int main_idx(int ch, int n1p, int n2, int kyl)
   {
-    return ((ch * (R1 / 2) + n1p) * R2 + n2) * KC + kyl;
+    return ((ch * (R1 / 2) + n1p) * KC + kyl) * R2 + n2;
+  }
+  // inverse of main_idx / of the tail numbering: float4 index i -> (n1p, n2, ky)
+  __host__ __device__ static void decode(int i, int &n1p, int &n2, int &ky)
+  {
+    if (i < MAIN4)
+    {
+      n2 = i % R2;
+      int t = i / R2;
+      const int kyl = t % KC;
+      t /= KC;
+      n1p = t % (R1 / 2);
+      ky = (t / (R1 / 2)) * KC + kyl;
+    }
+    else
+    {
+      const int t = i - MAIN4;
+      n2 = t % R2;
+      n1p = t / R2;
+      ky = NCOL;
+    }
   }
 };
 
@@ -110,23 +130,7 @@ __global__ void pack_kernel(const float2 *__restrict__ std_maps, float4 *__restr
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L::MAP4; i += gridDim.x * blockDim.x)
   {
     int n1p, n2, ky;
-    if (i < L::MAIN4)
-    {
-      int kyl = i % L::KC;
-      int t = i / L::KC;
-      n2 = t % L::R2;
-      t /= L::R2;
-      n1p = t % (L::R1 / 2);
-      int ch = t / (L::R1 / 2);
-      ky = ch * L::KC + kyl;
-    }
-    else
-    {
-      int t = i - L::MAIN4;
-      n2 = t % L::R2;
-      n1p = t / L::R2;
-      ky = L::NCOL;
-    }
+    L::decode(i, n1p, n2, ky);
     const int kx0 = (2 * n1p) * L::R2 + n2, kx1 = (2 * n1p + 1) * L::R2 + n2;
     float2 a = src[(size_t) kx0 * (N / 2 + 1) + ky], b = src[(size_t) kx1 * (N / 2 + 1) + ky];
     dst[i] = make_float4(a.x, a.y, b.x, b.y);
@@ -145,23 +149,7 @@ __global__ void unpack_kernel(const float4 *__restrict__ packed, float2 *__restr
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L::MAP4; i += gridDim.x * blockDim.x)
   {
     int n1p, n2, ky;
-    if (i < L::MAIN4)
-    {
-      int kyl = i % L::KC;
-      int t = i / L::KC;
-      n2 = t % L::R2;
-      t /= L::R2;
-      n1p = t % (L::R1 / 2);
-      int ch = t / (L::R1 / 2);
-      ky = ch * L::KC + kyl;
-    }
-    else
-    {
-      int t = i - L::MAIN4;
-      n2 = t % L::R2;
-      n1p = t / L::R2;
-      ky = L::NCOL;
-    }
+    L::decode(i, n1p, n2, ky);
     const int kx0 = (2 * n1p) * L::R2 + n2, kx1 = (2 * n1p + 1) * L::R2 + n2;
     float4 v = src[i];
     dst[(size_t) kx0 * (N / 2 + 1) + ky] = make_float2(v.x, v.y);
@@ -527,7 +515,9 @@ __global__ void __launch_bounds__(NT) ctf_conv_kernel(const float4 *__restrict__
     // Hermitian weights (bioem.cpp:1893-1914): 1 for ky = 0 and ky = N/2, else 2
     float w = 2.f;
     const bool tail = i >= L::MAIN4;
-    const bool dc = !tail && (i % L::KC) == 0 && (i / (L::KC * L::R2 * (L::R1 / 2))) == 0;
+    int n1p, n2, ky;
+    L::decode(i, n1p, n2, ky);
+    const bool dc = ky == 0;
     if (tail || dc)
       w = 1.f;
     float4 vs = v;
@@ -538,8 +528,6 @@ __global__ void __launch_bounds__(NT) ctf_conv_kernel(const float4 *__restrict__
       // the Hermitian part of these columns: Re of their kx-transform.  Store that part,
       // V_sym[kx] = (V[kx] + conj V[-kx]) / 2, so that the fused kernel can pack the two
       // columns into one complex transform.  sumC / sumsquareC use the unsymmetrised V.
-      const int t = tail ? i - L::MAIN4 : i / L::KC; // = n1p * R2 + n2
-      const int n2 = t % L::R2, n1p = t / L::R2;
       float pv[4];
 #pragma unroll
       for (int e = 0; e < 2; e++)
@@ -608,39 +596,47 @@ struct LikParams
   int nwp; // nw rounded up to even
   float Ntotpi;
   float invNN;
-  float acoef_f; // (3 - Nt)/2
+  float ex2coef; // (3 - Nt)/2 * log2(e): sum of exp over the window runs in base 2
   double acoef_d;
-  float tcut; // relative firstele excess beyond which exp() underflows to nothing
 };
 
-// Shared-memory plan of the fused kernel.
-//   Y   [nwp][YS]  window rows of the column-transformed spectrum (float2); YS = NCOL + pad so
-//                  that consecutive rows fall into different banks
-//   E   per warp [R1][ES] exchange buffer of the column pass (float2); aliased by FE [nw*nw]
-//   TW  [N] twiddles, WT [N] window table
+// number of leading (= trailing) radix-R2 output groups that can hold a displacement of
+// [-maxD, maxD]: raw index k = k1 + R1*k2, k <= maxD or k >= N - maxD
+template <int N> __host__ __device__ constexpr int lik_window_groups(int maxD)
+{
+  using L = Lay<N>;
+  constexpr int HALF = L::R2 / 2;
+  const int need = maxD / L::R1 + 1;
+  return (need <= 4 && need < HALF) ? need : HALF;
+}
+
+// Shared-memory plan of the fused kernel (W = window groups, NK = kept radix-R2 outputs).
+//   Y   [NK*R1][YS] float2: rows of the column-transformed spectrum that can hold window
+//       displacements, row slot = j*R1 + k1 for raw row k1 + R1*k2(j).  After a row pair has been
+//       consumed by the row pass its two slots are reused for the pair's firstele values
+//       (FE, NK*R1 floats per window row).
+//   E   per warp [R1][ES] float2: the exchange tile between the two radix passes
+//   WT  [N] window table, RS [256] window row -> row slot
 template <int N> struct LikSmem
 {
   using L = Lay<N>;
   static constexpr int NWARP = NT / 32;
   static constexpr int KC = L::KC;
-  // pass-2 lanes are (k1, kyl): address k1*ES + kyl -> distinct bank pairs in a half warp
+  // pass-2 lanes are (k1, c): address k1*ES + c must fall into distinct bank pairs in a half warp
   static constexpr int ES = L::R2 * KC + ((KC - L::R2 * KC) % 16 + 16) % 16;
-  static constexpr int YS = L::NCOL + ((KC - L::NCOL) % 16 + 16) % 16 + (N - 2 * (L::NCOL + ((KC - L::NCOL) % 16 + 16) % 16) > 0 ? 16 : 0);
-  static_assert(2 * YS >= N, "a row pair must hold one N-point transform in place");
-  static constexpr int EW = L::R1 * ES; // float2 per warp
-  __host__ __device__ static constexpr size_t ex_floats(int nw)
+  static constexpr int YS0 = L::NCOL + ((KC - L::NCOL) % 16 + 16) % 16;
+  static constexpr int YS = YS0 > L::NCOL ? YS0 : YS0 + 16; // index NCOL of a row must exist
+  static constexpr int EW = L::R1 * ES;                     // float2 per warp
+  __host__ __device__ static constexpr int nk(int W) { return 2 * W >= L::R2 ? L::R2 : 2 * W; }
+  __host__ __device__ static constexpr size_t bytes(int W)
   {
-    size_t e = (size_t) NWARP * EW * 2, f = (size_t) nw * nw;
-    size_t x = e > f ? e : f;
-    return (x + 3) & ~(size_t) 3;
-  }
-  __host__ __device__ static constexpr size_t bytes(int nw)
-  {
-    const int nwp = nw + (nw & 1);
-    return ((size_t) nwp * YS * 2 + ex_floats(nw) + (size_t) N * 2) * sizeof(float) + ((N + 15) & ~15);
+    return ((size_t) nk(W) * L::R1 * YS + (size_t) NWARP * EW) * sizeof(float2) + ((N + 15) & ~15) + 256;
   }
 };
-template <int N> __host__ __device__ constexpr size_t lik_smem_bytes(int nw) { return LikSmem<N>::bytes(nw); }
+template <int N> __host__ __device__ constexpr size_t lik_smem_bytes(int maxD)
+{
+  return LikSmem<N>::bytes(lik_window_groups<N>(maxD));
+}
 
 __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int m)
 {
@@ -650,6 +646,16 @@ __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v,
   return ((unsigned long long) hi << 32) | lo;
 }
 
+constexpr int NCAND = 48; // near-minimum candidates examined exactly per likelihood
+
+// running per-image state of one CTA (kept in shared memory, touched by thread 0 only)
+struct BookState
+{
+  double Const, Total, anConst, anTotal;
+  float lpf, v, sC, ssC;
+  int o, c, lin;
+};
+
 // ===========================================================================
 // stages 3-5 fused.  One CTA owns one particle image m and a group of
 // orientations of the current batch; for every (orientation, CTF) pair it
@@ -657,40 +663,48 @@ __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v,
 //     coalesced 128-bit loads (one 512-byte line per warp instruction) and multiplies
 //     conv * conj(particle) in registers,
 //   * column pass of the inverse 2-D FFT, WARP-SYNCHRONOUS: each warp owns KC columns at a
-//     time (lanes = R2 sub-sequences x KC columns), radix-R1 in registers, twiddle, exchange
-//     through the warp's private shared-memory tile (only __syncwarp), radix-R2 in registers;
-//     only the displacement-window rows are kept (output pruning),
-//   * row pass, also warp-synchronous: two real rows per complex transform, in place,
+//     time (lanes = KC columns x R2 sub-sequences), radix-R1 in registers, twiddle (lane
+//     constants held in registers), exchange through the warp's private shared-memory tile
+//     (only __syncwarp), radix-R2 in registers; only the output groups that can hold window
+//     displacements are formed (output pruning) and stored, unconditionally, as rows of Y,
+//   * row pass, same structure: two real rows per complex transform, through the same tile,
 //   * the displacement-dependent factor of the analytic log-posterior (firstele, FP32,
-//     reference operation order) straight out of the FFT registers; (min firstele <=> max
-//     logpro, sum of exp) reduced in the CTA,
-//   * the image's running (Constoadd, Total, arg-max) kept in registers of one thread.
-// Three CTA-wide barriers per likelihood; no correlation map ever leaves the SM.
+//     reference operation order, two displacements per packed instruction) straight out of
+//     the FFT registers into the consumed row slots; min firstele (<=> max logpro) per CTA,
+//   * sum of exp over the window relative to that minimum, and the displacements whose
+//     firstele is within a few ulps of it (they can share the float-narrowed logpro; the
+//     reference keeps the FIRST of them, bioem_algorithm.h:84-96),
+//   * the image's running (Constoadd, Total, arg-max) updated by one thread.
+// All butterflies run on packed FP32x2 instructions.  Three CTA-wide barriers per
+// likelihood; no correlation map ever leaves the SM.
 // ===========================================================================
-// W = number of leading and of trailing radix-R2 output groups k2 that can hold window
-// displacements (k2 < W or k2 >= R2 - W); outputs of the other groups are never formed
-// (the compiler prunes the butterflies that only feed them).  2W >= R2 keeps everything.
 template <int N, int W> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)) likelihood_kernel(LikParams p)
 {
   using L = Lay<N>;
   using SM = LikSmem<N>;
-  constexpr int NK = (2 * W >= L::R2) ? L::R2 : 2 * W; // output groups kept
-  constexpr int NKW = (NK + 3) / 4;                    // 32-bit words of a per-lane byte table
+  constexpr int NK = SM::nk(W); // radix-R2 output groups kept
   constexpr int R1 = L::R1, R2 = L::R2, KC = L::KC, NCOL = L::NCOL, NCH = L::NCH;
   constexpr int ES = SM::ES, YS = SM::YS, NWARP = SM::NWARP;
-  constexpr int PW = KC;             // row pairs per warp task (lanes = PW x R2)
-  constexpr int P2 = (KC * R1 + 31) / 32; // pass-2 trips
+  constexpr int NROWS = NK * R1;              // row slots of Y = firstele values per window row
+  constexpr int P2 = (KC * R1 + 31) / 32;     // pass-2 trips
+  constexpr int CP = NROWS / 2;               // float2 column pairs of a firstele row
+  constexpr int RG = NT / CP > 0 ? NT / CP : 1; // row groups of the exp-sum sweep
+  static_assert(CP <= NT, "one thread per firstele column pair");
+  auto k2_of = [](int j) { return (NK == R2) ? j : (j < W ? j : R2 - NK + j); };
+
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int nw = p.nw, nwp = p.nwp;
-  float2 *Y = reinterpret_cast<float2 *>(smem_raw); // [nwp][YS]
-  float2 *Eall = Y + (size_t) nwp * YS;
-  float *FE = reinterpret_cast<float *>(Eall);
-  float2 *TW = reinterpret_cast<float2 *>(FE + SM::ex_floats(nw));
-  unsigned char *WT = reinterpret_cast<unsigned char *>(TW + N);
+  float2 *Y = reinterpret_cast<float2 *>(smem_raw); // [NROWS][YS]
+  float2 *Eall = Y + (size_t) NROWS * YS;
+  unsigned char *WT = reinterpret_cast<unsigned char *>(Eall + (size_t) NWARP * SM::EW);
+  unsigned char *RS = WT + ((N + 15) & ~15);
   __shared__ unsigned long long s_key[2];
   __shared__ float s_wsum[2][NWARP];
   __shared__ float s_winv[2];
+  __shared__ int s_ncand[2];
+  __shared__ uint2 s_cand[2][NCAND];
+  __shared__ BookState s_bk;
 
+  const int nw = p.nw, nwp = p.nwp;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float2 *E = Eall + (size_t) warp * SM::EW;
   const int m = blockIdx.x % p.M;
@@ -700,59 +714,66 @@ template <int N, int W> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)
 
   for (int i = tid; i < N; i += NT)
   {
-    TW[i] = p.tw_inv[i];
-    WT[i] = p.wtab[i];
+    const unsigned w = p.wtab[i];
+    WT[i] = (unsigned char) w;
+    if (w != 255u)
+    {
+      const int k2 = i / R1, k1 = i % R1;
+      const int j = (NK == R2) ? k2 : (k2 < W ? k2 : k2 - (R2 - NK));
+      RS[w] = (unsigned char) (j * R1 + k1);
+      if ((int) w == nw - 1)
+        RS[nw] = (unsigned char) (j * R1 + k1); // padding row of an odd window: any valid slot
+    }
   }
   if (tid < 2)
+  {
     s_key[tid] = ~0ull;
+    s_ncand[tid] = 0;
+  }
+  if (tid == 0)
+  {
+    s_bk.Const = kMinProb;
+    s_bk.Total = 0.0;
+    s_bk.lpf = 0.f;
+    s_bk.v = s_bk.sC = s_bk.ssC = 0.f;
+    s_bk.o = s_bk.c = s_bk.lin = 0;
+  }
   __syncthreads();
 
-  // lane roles (fixed for the whole kernel)
-  const int c1_n2 = lane / KC, c1_ky = lane % KC; // column pass 1: (sub-sequence, column)
-  const bool c1_act = lane < R2 * KC;
-  const int r1_pl = lane / R2, r1_n2 = lane % R2; // row pass 1: (pair, sub-sequence)
-  const bool r1_act = lane < PW * R2;
-  // per-lane tables: window index (byte, 255 = not a window displacement) of raw index
-  // k1 + R1*k2 for the kept k2, for this lane's k1 in the column role and in the row role
-  unsigned ctab[P2][NKW], rtab[P2][NKW];
+  // lane roles (fixed for the whole kernel).  Pass 1 of both transforms: lane = c*R2 + n2
+  // (c = column / row pair within the warp's task, n2 = sub-sequence).  Pass 2: item = k1*KC + c.
+  const int a_c = lane / R2, a_n2 = lane % R2;
+  const bool a_act = lane < KC * R2;
+  float2 tw[R1]; // exp(+2 pi i n2*k1/N), k1 >= 1
+#pragma unroll
+  for (int k1 = 1; k1 < R1; k1++)
+    tw[k1] = p.tw_inv[a_n2 * R1 + k1];
+  // firstele penalty of this lane's pass-2 outputs: +inf where the raw column index is not a
+  // window displacement (those entries then drop out of the minimum and of the sum)
+  float pen[P2][NK];
 #pragma unroll
   for (int t = 0; t < P2; t++)
   {
     const int item = lane + 32 * t;
-    const bool act = item < KC * R1;
-    const int kc = item / KC; // column pass 2: item = k1*KC + kyl
-    const int kr = item % R1; // row pass 2:    item = pl*R1 + k1
-#pragma unroll
-    for (int w = 0; w < NKW; w++)
-    {
-      ctab[t][w] = 0xffffffffu;
-      rtab[t][w] = 0xffffffffu;
-    }
+    const int k1 = (item / KC) % R1;
     bfft::static_for<0, NK>([&](auto j_) {
       constexpr int j = decltype(j_)::value;
-      constexpr int k2 = (NK == R2) ? j : (j < W ? j : R2 - NK + j);
-      const unsigned bc = act ? WT[kc + R1 * k2] : 255u;
-      const unsigned br = act ? WT[kr + R1 * k2] : 255u;
-      ctab[t][j / 4] = (ctab[t][j / 4] & ~(0xffu << (8 * (j % 4)))) | (bc << (8 * (j % 4)));
-      rtab[t][j / 4] = (rtab[t][j / 4] & ~(0xffu << (8 * (j % 4)))) | (br << (8 * (j % 4)));
+      pen[t][j] = WT[k1 + R1 * k2_of(j)] == 255 ? __int_as_float(0x7f800000) : 0.f;
     });
   }
 
   const float4 *ref = p.refs + (size_t) m * L::MAP4;
   const float sR = p.sumRef[m], ssR = p.sumsqRef[m];
   const float Nt = p.Ntotpi;
-
-  // bookkeeping state (meaningful in thread 0 only)
-  double bk_Const = kMinProb, bk_Total = 0.0;
-  float bk_lpf = 0.f, bk_v = 0.f, bk_sC = 0.f, bk_ssC = 0.f;
-  int bk_o = 0, bk_c = 0, bk_lin = 0;
-  double an_Const = kMinProb, an_Total = 0.0;
   int buf = 0;
 
   for (int ol = o_lo; ol < o_hi; ol++)
   {
-    an_Const = kMinProb;
-    an_Total = 0.0;
+    if (tid == 0)
+    {
+      s_bk.anConst = kMinProb;
+      s_bk.anTotal = 0.0;
+    }
     for (int c = 0; c < p.C; c++)
     {
       const int oc = ol * p.C + c;
@@ -767,41 +788,37 @@ template <int N, int W> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)
       // ------------------------------------------------ column pass (along kx), per warp
       for (int ch = warp; ch < NCH; ch += NWARP)
       {
-        if (c1_act)
+        if (a_act)
         {
           float2 x[R1];
-          const int base = ch * (R1 / 2) * R2 * KC + lane; // == main_idx(ch, 0, c1_n2, c1_ky)
+          const int base = ch * (R1 / 2) * KC * R2 + lane; // == main_idx(ch, 0, a_n2, a_c)
 #pragma unroll
           for (int n1p = 0; n1p < R1 / 2; n1p++)
           {
-            const float4 r = ldg4(ref + base + n1p * R2 * KC);
-            const float4 v = ldg4(conv + base + n1p * R2 * KC);
+            const float4 r = ldg4(ref + base + n1p * KC * R2);
+            const float4 v = ldg4(conv + base + n1p * KC * R2);
             x[2 * n1p] = bfft::cmulc(make_float2(v.x, v.y), make_float2(r.x, r.y));
             x[2 * n1p + 1] = bfft::cmulc(make_float2(v.z, v.w), make_float2(r.z, r.w));
           }
-          if (ch == 0 && c1_ky == 0)
+          if (ch == 0 && a_c == 0)
           {
             // pack the Nyquist column into the (Hermitian) DC column: Z = X0 + i*X_{N/2}
 #pragma unroll
             for (int n1p = 0; n1p < R1 / 2; n1p++)
             {
-              const float4 r = ldg4(ref + L::MAIN4 + n1p * R2 + c1_n2);
-              const float4 v = ldg4(conv + L::MAIN4 + n1p * R2 + c1_n2);
-              const float2 t0 = bfft::cmulc(make_float2(v.x, v.y), make_float2(r.x, r.y));
-              const float2 t1 = bfft::cmulc(make_float2(v.z, v.w), make_float2(r.z, r.w));
-              x[2 * n1p].x -= t0.y;
-              x[2 * n1p].y += t0.x;
-              x[2 * n1p + 1].x -= t1.y;
-              x[2 * n1p + 1].y += t1.x;
+              const float4 r = ldg4(ref + L::MAIN4 + n1p * R2 + a_n2);
+              const float4 v = ldg4(conv + L::MAIN4 + n1p * R2 + a_n2);
+              x[2 * n1p] = bfft::cadd_i(x[2 * n1p], bfft::cmulc(make_float2(v.x, v.y), make_float2(r.x, r.y)));
+              x[2 * n1p + 1] = bfft::cadd_i(x[2 * n1p + 1], bfft::cmulc(make_float2(v.z, v.w), make_float2(r.z, r.w)));
             }
           }
           bfft::Dft<R1, 1>::run(x);
 #pragma unroll
           for (int k1 = 1; k1 < R1; k1++)
-            x[k1] = bfft::cmul(x[k1], TW[c1_n2 * R1 + k1]);
+            x[k1] = bfft::cmul(x[k1], tw[k1]);
 #pragma unroll
           for (int k1 = 0; k1 < R1; k1++)
-            E[k1 * ES + lane] = x[k1];
+            E[k1 * ES + a_n2 * KC + a_c] = x[k1];
         }
         __syncwarp();
 #pragma unroll
@@ -810,147 +827,131 @@ template <int N, int W> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)
           const int item = lane + 32 * t;
           if (item < KC * R1)
           {
-            const int k1 = item / KC, kyl = item % KC;
+            const int k1 = item / KC, cc = item % KC;
             float2 y[R2];
 #pragma unroll
             for (int n2 = 0; n2 < R2; n2++)
-              y[n2] = E[k1 * ES + n2 * KC + kyl];
+              y[n2] = E[k1 * ES + n2 * KC + cc];
             bfft::Dft<R2, 1>::run(y);
-            float2 *Ycol = Y + ch * KC + kyl;
+            float2 *Ycol = Y + k1 * YS + ch * KC + cc;
             bfft::static_for<0, NK>([&](auto j_) {
               constexpr int j = decltype(j_)::value;
-              constexpr int k2 = (NK == R2) ? j : (j < W ? j : R2 - NK + j);
-              const unsigned w = (ctab[t][j / 4] >> (8 * (j % 4))) & 0xffu;
-              if (w != 255u)
-                Ycol[w * YS] = y[k2];
+              Ycol[j * R1 * YS] = y[k2_of(j)];
             });
           }
         }
         __syncwarp();
       }
-      __syncthreads(); // window rows of all columns are in Y
+      __syncthreads(); // all candidate rows of all columns are in Y
 
       // ------------------------------------------------ row pass (along ky), 2 rows per transform
-      unsigned long long best = ~0ull;
-      float best_v = 0.f;
+      float bfe = __int_as_float(0x7f800000), bv = 0.f;
+      int blin = 0x7fffffff;
       const int npairs = nwp / 2;
-      for (int p0 = warp * PW; p0 < npairs; p0 += NWARP * PW)
+      for (int p0 = warp * KC; p0 < npairs; p0 += NWARP * KC)
       {
-        const int npl = min(PW, npairs - p0);
-        if ((nw & 1) && p0 + npl == npairs)
+        const int npl = min(KC, npairs - p0);
+        if (a_act && a_c < npl)
         {
-          // zero the padding row of the last pair (it holds leftovers of the previous transform)
-          for (int i = lane; i < NCOL; i += 32)
-            Y[(size_t) nw * YS + i] = make_float2(0.f, 0.f);
-          __syncwarp();
-        }
-        float2 x[R1];
-        const bool act1 = r1_act && r1_pl < npl;
-        float2 *Yp = Y + (size_t) (2 * (p0 + r1_pl)) * YS; // rows a, b; the pair region holds N points
-        if (act1)
-        {
-          const float2 *Ya = Yp, *Yb = Yp + YS;
-          const int n2 = r1_n2;
+          const float2 *Ya = Y + (size_t) RS[2 * (p0 + a_c)] * YS;
+          const float2 *Yb = Y + (size_t) RS[2 * (p0 + a_c) + 1] * YS;
+          float2 x[R1];
 #pragma unroll
           for (int n1 = 0; n1 < R1; n1++)
           {
             if (n1 < R1 / 2)
             {
-              const float2 a = Ya[n1 * R2 + n2], b = Yb[n1 * R2 + n2];
-              if (n1 == 0 && n2 == 0)
-                x[n1] = make_float2(a.x, b.x);
-              else
-                x[n1] = make_float2(a.x - b.y, a.y + b.x);
+              const float2 a = Ya[n1 * R2 + a_n2], b = Yb[n1 * R2 + a_n2];
+              x[n1] = bfft::cadd_i(a, b); // A[n] + i*B[n]
             }
             else
             {
-              // n = n1*R2 + n2 >= N/2: mirrored element n' = N - n
-              const int nm = (R1 - n1) * R2 - n2;
-              if (n1 == R1 / 2 && n2 == 0)
-              {
-                const float2 a = Ya[0], b = Yb[0];
-                x[n1] = make_float2(a.y, b.y); // Nyquist, packed in the DC slot's imaginary part
-              }
-              else
-              {
-                const float2 a = Ya[nm], b = Yb[nm];
-                x[n1] = make_float2(a.x + b.y, b.x - a.y);
-              }
+              // n = n1*R2 + n2 >= N/2: A[n] = conj(A[N-n])
+              const int nm = (R1 - n1) * R2 - a_n2;
+              const float2 a = Ya[nm], b = Yb[nm];
+              x[n1] = __fadd2_rn(make_float2(a.x, -a.y), make_float2(b.y, b.x));
             }
+          }
+          if (a_n2 == 0)
+          {
+            // DC and Nyquist of the two (real) columns ky = 0 and ky = N/2 share slot 0
+            const float2 a = Ya[0], b = Yb[0];
+            x[0] = make_float2(a.x, b.x);
+            x[R1 / 2] = make_float2(a.y, b.y);
           }
           bfft::Dft<R1, 1>::run(x);
 #pragma unroll
           for (int k1 = 1; k1 < R1; k1++)
-            x[k1] = bfft::cmul(x[k1], TW[n2 * R1 + k1]);
-        }
-        __syncwarp(); // all reads of this task's rows are done: overwrite in place
-        if (act1)
-        {
+            x[k1] = bfft::cmul(x[k1], tw[k1]);
 #pragma unroll
           for (int k1 = 0; k1 < R1; k1++)
-            Yp[k1 * R2 + ((r1_n2 + k1) % R2)] = x[k1];
+            E[k1 * ES + a_n2 * KC + a_c] = x[k1];
         }
-        __syncwarp();
+        __syncwarp(); // also: every read of this task's Y rows is done, their slots may take FE
 #pragma unroll
         for (int t = 0; t < P2; t++)
         {
           const int item = lane + 32 * t;
-          const int pl = item / R1, k1 = item % R1;
-          if (item < KC * R1 && pl < npl)
+          const int k1 = item / KC, cc = item % KC;
+          if (item < KC * R1 && cc < npl)
           {
-            const float2 *Yq = Y + (size_t) (2 * (p0 + pl)) * YS;
             float2 y[R2];
 #pragma unroll
-            for (int n2b = 0; n2b < R2; n2b++)
-              y[n2b] = Yq[k1 * R2 + ((n2b + k1) % R2)];
+            for (int n2 = 0; n2 < R2; n2++)
+              y[n2] = E[k1 * ES + n2 * KC + cc];
             bfft::Dft<R2, 1>::run(y);
-            const int wa = 2 * (p0 + pl), wb = wa + 1;
-            const bool vb = wb < nw;
+            const int wa = 2 * (p0 + cc);
+            const bool vb = wa + 1 < nw;
+            float *FEa = reinterpret_cast<float *>(Y + (size_t) RS[wa] * YS) + k1;
+            float *FEb = reinterpret_cast<float *>(Y + (size_t) RS[wa + 1] * YS) + k1;
             bfft::static_for<0, NK>([&](auto j_) {
               constexpr int j = decltype(j_)::value;
-              constexpr int k2 = (NK == R2) ? j : (j < W ? j : R2 - NK + j);
-              const unsigned wy = (rtab[t][j / 4] >> (8 * (j % 4))) & 0xffu;
-              const bool in = wy != 255u;
+              // .x = row wa, .y = row wa + 1
+              const float2 v = bfft::cscale(y[k2_of(j)], p.invNN);
+              float2 fe = __fmul2_rn(v, v);
+              fe = __fadd2_rn(make_float2(f_a, f_a), make_float2(-fe.x, -fe.y));
+              fe = __fmul2_rn(make_float2(Nt, Nt), fe);
+              fe = __fadd2_rn(fe, __fmul2_rn(make_float2(f_b, f_b), v));
+              fe = __fadd2_rn(fe, make_float2(-f_c, -f_c));
+              fe = __fadd2_rn(fe, make_float2(-f_d, -f_d));
+              fe = __fadd2_rn(fe, make_float2(pen[t][j], pen[t][j]));
+              FEa[j * R1] = fe.x;
+              if (vb)
+                FEb[j * R1] = fe.y;
+              if (fe.x <= bfe || (vb && fe.y <= bfe))
               {
-                const float v = y[k2].x * p.invNN;
-                const float fe = __fsub_rn(__fsub_rn(__fadd_rn(__fmul_rn(Nt, __fsub_rn(f_a, __fmul_rn(v, v))), __fmul_rn(f_b, v)), f_c), f_d);
-                const int lin = wa * nw + (int) wy;
-                const unsigned long long key = ((unsigned long long) __float_as_uint(fe) << 32) | (unsigned) lin;
-                if (in)
+                // rare: a new per-thread minimum (ties resolved by the enumeration index)
+                const int wy = WT[k1 + R1 * k2_of(j)];
+                const int la = wa * nw + wy, lb = la + nw;
+                if (fe.x < bfe || (fe.x == bfe && la < blin))
                 {
-                  FE[lin] = fe;
-                  if (key < best)
-                  {
-                    best = key;
-                    best_v = v;
-                  }
-                  if (p.dbg_values)
-                    p.dbg_values[((size_t) oc * p.M + m) * nw * nw + lin] = v;
+                  bfe = fe.x;
+                  blin = la;
+                  bv = v.x;
+                }
+                if (vb && (fe.y < bfe || (fe.y == bfe && lb < blin)))
+                {
+                  bfe = fe.y;
+                  blin = lb;
+                  bv = v.y;
                 }
               }
+              if (p.dbg_values && pen[t][j] == 0.f)
               {
-                const float v = y[k2].y * p.invNN;
-                const float fe = __fsub_rn(__fsub_rn(__fadd_rn(__fmul_rn(Nt, __fsub_rn(f_a, __fmul_rn(v, v))), __fmul_rn(f_b, v)), f_c), f_d);
-                const int lin = wb * nw + (int) wy;
-                const unsigned long long key = ((unsigned long long) __float_as_uint(fe) << 32) | (unsigned) lin;
-                if (in && vb)
-                {
-                  FE[lin] = fe;
-                  if (key < best)
-                  {
-                    best = key;
-                    best_v = v;
-                  }
-                  if (p.dbg_values)
-                    p.dbg_values[((size_t) oc * p.M + m) * nw * nw + lin] = v;
-                }
+                const int wy = WT[k1 + R1 * k2_of(j)];
+                float *dv = p.dbg_values + ((size_t) oc * p.M + m) * nw * nw;
+                dv[wa * nw + wy] = v.x;
+                if (vb)
+                  dv[(wa + 1) * nw + wy] = v.y;
               }
             });
           }
         }
+        __syncwarp();
       }
 
-      // ------------------------------------------------ reduce over the displacement window
+      // ------------------------------------------------ minimum over the displacement window
+      const unsigned long long best = ((unsigned long long) __float_as_uint(bfe) << 32) | (unsigned) blin;
       unsigned long long wbest = best;
 #pragma unroll
       for (int s = 16; s > 0; s >>= 1)
@@ -964,59 +965,99 @@ template <int N, int W> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)
       const unsigned long long kmin = s_key[buf];
       const float fmin = __uint_as_float((unsigned) (kmin >> 32));
       if (best == kmin)
-        s_winv[buf] = best_v;
+        s_winv[buf] = bv;
+      // every firstele within NEAR ulps of the minimum may share its float-narrowed logpro
+      const float fthr = __uint_as_float((unsigned) (kmin >> 32) + 64u);
       const float inv = __fdiv_rn(1.0f, fmin);
-      float S = 0.f;
-      for (int i = tid; i < nw * nw; i += NT)
+      float2 S2 = make_float2(0.f, 0.f);
+      if (tid < RG * CP)
       {
-        const float t = (FE[i] - fmin) * inv;
-        if (t < p.tcut)
+        const int cpi = tid % CP, rg = tid / CP;
+        const float c1 = p.ex2coef, c2 = -0.5f * p.ex2coef, c3 = p.ex2coef * (1.f / 3.f);
+        for (int wx = rg; wx < nw; wx += RG)
         {
-          // log1p(t) for tiny t >= 0
-          const float l = t * (1.f - t * (0.5f - t * (1.f / 3.f)));
-          S += __expf(p.acoef_f * l);
+          const float2 f = reinterpret_cast<const float2 *>(Y + (size_t) RS[wx] * YS)[cpi];
+          // exp(a*log1p(t)), t = (fe - fmin)/fmin >= 0 tiny where it matters; +inf -> 0
+          const float2 t = __fmul2_rn(__fadd2_rn(f, make_float2(-fmin, -fmin)), make_float2(inv, inv));
+          float2 l = __ffma2_rn(t, make_float2(c3, c3), make_float2(c2, c2));
+          l = __ffma2_rn(t, l, make_float2(c1, c1));
+          l = __fmul2_rn(t, l);
+          S2 = __fadd2_rn(S2, make_float2(exp2f(l.x), exp2f(l.y)));
+          if (f.x <= fthr || f.y <= fthr)
+          {
+#pragma unroll
+            for (int e = 0; e < 2; e++)
+            {
+              const float fv = e ? f.y : f.x;
+              if (fv <= fthr)
+              {
+                const int col = 2 * cpi + e;
+                const int jj = col / R1, k1 = col % R1;
+                const int k2 = (NK == R2) ? jj : (jj < W ? jj : R2 - NK + jj);
+                const int lin = wx * nw + WT[k1 + R1 * k2];
+                const int slot = atomicAdd(&s_ncand[buf], 1);
+                if (slot < NCAND)
+                  s_cand[buf][slot] = make_uint2(__float_as_uint(fv), (unsigned) lin);
+              }
+            }
+          }
         }
       }
+      float S = S2.x + S2.y;
 #pragma unroll
       for (int s = 16; s > 0; s >>= 1)
         S += __shfl_xor_sync(0xffffffffu, S, s);
       if (lane == 0)
         s_wsum[buf][warp] = S;
-      __syncthreads(); // FE consumed (E may be overwritten), partial sums visible
+      __syncthreads(); // FE consumed (Y may be overwritten), partial sums and candidates visible
 
       // ------------------------------------------------ bookkeeping (bioem_algorithm.h:84-141)
       if (tid == 0)
       {
-        s_key[buf ^ 1] = ~0ull;
         float Ssum = 0.f;
 #pragma unroll
         for (int w = 0; w < NWARP; w++)
           Ssum += s_wsum[buf][w];
         const double lp = p.acoef_d * log((double) fmin) + cp.Bterm;
         const float lpf = (float) lp;
-        if (bk_Const < (double) lpf)
+        int lin = (int) (kmin & 0xffffffffu);
+        const int nc = s_ncand[buf];
+        if (nc <= NCAND)
+          for (int i = 0; i < nc; i++)
+          {
+            const uint2 cd = s_cand[buf][i];
+            if ((int) cd.y < lin)
+            {
+              const float lc = (float) (p.acoef_d * log((double) __uint_as_float(cd.x)) + cp.Bterm);
+              if (lc == lpf)
+                lin = (int) cd.y;
+            }
+          }
+        s_key[buf ^ 1] = ~0ull;
+        s_ncand[buf ^ 1] = 0;
+        if (s_bk.Const < (double) lpf)
         {
-          bk_Total = bk_Total * exp(bk_Const - (double) lpf) + (double) Ssum;
-          bk_Const = (double) lpf;
-          bk_lpf = lpf;
-          bk_o = p.o_base + ol;
-          bk_c = c;
-          bk_lin = (int) (kmin & 0xffffffffu);
-          bk_v = s_winv[buf];
-          bk_sC = cp.sumC;
-          bk_ssC = cp.sumsqC;
+          s_bk.Total = s_bk.Total * exp(s_bk.Const - (double) lpf) + (double) Ssum;
+          s_bk.Const = (double) lpf;
+          s_bk.lpf = lpf;
+          s_bk.o = p.o_base + ol;
+          s_bk.c = c;
+          s_bk.lin = lin;
+          s_bk.v = s_winv[buf];
+          s_bk.sC = cp.sumC;
+          s_bk.ssC = cp.sumsqC;
         }
         else
-          bk_Total += (double) Ssum * exp((double) lpf - bk_Const);
+          s_bk.Total += (double) Ssum * exp((double) lpf - s_bk.Const);
         if (p.angles)
         {
-          if (an_Const < (double) lpf)
+          if (s_bk.anConst < (double) lpf)
           {
-            an_Total = an_Total * exp(an_Const - (double) lpf) + (double) Ssum;
-            an_Const = (double) lpf;
+            s_bk.anTotal = s_bk.anTotal * exp(s_bk.anConst - (double) lpf) + (double) Ssum;
+            s_bk.anConst = (double) lpf;
           }
           else
-            an_Total += (double) Ssum * exp((double) lpf - an_Const);
+            s_bk.anTotal += (double) Ssum * exp((double) lpf - s_bk.anConst);
         }
       }
       buf ^= 1;
@@ -1024,27 +1065,28 @@ template <int N, int W> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)
     if (tid == 0 && p.angles)
     {
       ProbAngleOut a;
-      a.forAngles = an_Total;
-      a.ConstAngle = an_Const;
+      a.forAngles = s_bk.anTotal;
+      a.ConstAngle = s_bk.anConst;
       p.angles[(size_t) (p.o_base + ol) * p.M + m] = a;
     }
   }
   if (tid == 0)
   {
     Running r;
-    r.Const = bk_Const;
-    r.Total = bk_Total;
-    r.lpf = bk_lpf;
-    r.orient = bk_o;
-    r.conv = bk_c;
-    r.lin = bk_lin;
-    r.v = bk_v;
-    r.sumC = bk_sC;
-    r.sumsqC = bk_ssC;
+    r.Const = s_bk.Const;
+    r.Total = s_bk.Total;
+    r.lpf = s_bk.lpf;
+    r.orient = s_bk.o;
+    r.conv = s_bk.c;
+    r.lin = s_bk.lin;
+    r.v = s_bk.v;
+    r.sumC = s_bk.sC;
+    r.sumsqC = s_bk.ssC;
     r.pad = 0;
     p.partials[(size_t) g * p.M + m] = r;
   }
 }
+
 
 #ifndef BIOEM_LIK_ONLY
 // fold the per-group partials of one batch into the running per-image state, in

@@ -139,15 +139,37 @@ template <int SIGN, int P, int Q> BFFT_D float2 cmul_root(float2 a)
     return __ffma2_rn(make_float2(-a.y, a.x), make_float2(s, s), __fmul2_rn(a, make_float2(c, c)));
 }
 
+BFFT_HD constexpr int pow2_part(int r)
+{
+  int p = 1;
+  while (r % 2 == 0)
+  {
+    r /= 2;
+    p *= 2;
+  }
+  return p;
+}
+BFFT_HD constexpr int gcd_of(int a, int b) { return b == 0 ? a : gcd_of(b, a % b); }
+// modular inverse of a modulo m (gcd(a, m) == 1)
+BFFT_HD constexpr int inv_mod(int a, int m)
+{
+  for (int x = 1; x < m; x++)
+    if ((a * x) % m == 1)
+      return x;
+  return 1;
+}
+// first factor A of the split R = A * B used by Dft<R>: the power-of-two part when R also
+// has an odd part (coprime split -> Good-Thomas, no twiddles), else 4 / 2 / smallest prime.
 BFFT_HD constexpr int pick_factor(int r)
 {
-  if (r % 4 == 0 && r > 4)
-    return 4;
-  if (r % 2 == 0 && r > 2)
-    return 2;
-  for (int p = 3; p * p <= r; p += 2)
-    if (r % p == 0)
-      return p;
+  const int p = pow2_part(r), q = r / p;
+  if (p > 1 && q > 1)
+    return p;
+  if (q == 1)
+    return r > 4 ? 4 : r;
+  for (int f = 3; f * f <= r; f += 2)
+    if (r % f == 0)
+      return f;
   return r; // prime
 }
 
@@ -230,27 +252,34 @@ template <int R, int SIGN> struct Dft<R, SIGN, R>
   }
 };
 
-// composite R = A * B (A = pick_factor(R)):
-//   n = n1*B + n2, k = k1 + A*k2
-//   X[k1 + A*k2] = sum_{n2} W_R^{n2*k1} W_B^{n2*k2} sum_{n1} x[n1*B+n2] W_A^{n1*k1}
+// composite R = A * B (A = pick_factor(R)).
+//   gcd(A, B) == 1: Good-Thomas prime-factor map, no twiddles:
+//       n = (B*n1 + A*n2) mod R,  k = (B*(B^-1 mod A)*k1 + A*(A^-1 mod B)*k2) mod R
+//   else Cooley-Tukey: n = n1*B + n2, k = k1 + A*k2,
+//       X[k1 + A*k2] = sum_{n2} W_R^{n2*k1} W_B^{n2*k2} sum_{n1} x[n1*B+n2] W_A^{n1*k1}
 template <int R, int SIGN, int A> struct Dft
 {
   static_assert(R % A == 0 && A > 1 && A < R, "bad factorisation");
   BFFT_D static void run(float2 *v)
   {
     constexpr int B = R / A;
+    constexpr bool PFA = gcd_of(A, B) == 1;
     float2 t[R]; // t[k1*B + n2]
     static_for<0, B>([&](auto n2_) {
       constexpr int n2 = decltype(n2_)::value;
       float2 a[A];
       static_for<0, A>([&](auto n1_) {
         constexpr int n1 = decltype(n1_)::value;
-        a[n1] = v[n1 * B + n2];
+        constexpr int n = PFA ? (B * n1 + A * n2) % R : n1 * B + n2;
+        a[n1] = v[n];
       });
       Dft<A, SIGN>::run(a);
       static_for<0, A>([&](auto k1_) {
         constexpr int k1 = decltype(k1_)::value;
-        t[k1 * B + n2] = cmul_root<SIGN, n2 * k1, R>(a[k1]);
+        if constexpr (PFA)
+          t[k1 * B + n2] = a[k1];
+        else
+          t[k1 * B + n2] = cmul_root<SIGN, n2 * k1, R>(a[k1]);
       });
     });
     static_for<0, A>([&](auto k1_) {
@@ -263,7 +292,8 @@ template <int R, int SIGN, int A> struct Dft
       Dft<B, SIGN>::run(b);
       static_for<0, B>([&](auto k2_) {
         constexpr int k2 = decltype(k2_)::value;
-        v[k1 + A * k2] = b[k2];
+        constexpr int k = PFA ? (B * inv_mod(B % A, A) * k1 + A * inv_mod(A % B, B) * k2) % R : k1 + A * k2;
+        v[k] = b[k2];
       });
     });
   }

@@ -7,7 +7,7 @@ namespace bioem
 {
 template <int W> static cudaError_t lik_launch_w(const LikParams &p, int nblocks, cudaStream_t s)
 {
-  const size_t smem = lik_smem_bytes<BIOEM_N>(p.nw);
+  const size_t smem = LikSmem<BIOEM_N>::bytes(W);
   // attribute is per device context: set on every launch (cheap next to the kernel)
   cudaError_t e = cudaFuncSetAttribute(likelihood_kernel<BIOEM_N, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
   if (e != cudaSuccess)
@@ -24,19 +24,18 @@ extern "C" cudaError_t BIOEM_CAT(bioem_lik_launch_, BIOEM_N)(const bioem::LikPar
 {
   using L = bioem::Lay<BIOEM_N>;
   constexpr int HALF = L::R2 / 2;
-  // radix-R2 output groups that can hold a displacement in [-maxD, maxD]:
-  // k2 <= maxD/R1 at the low end, k2 >= R2 - ceil(maxD/R1) at the high end
-  const int need = maxD / L::R1 + 1;
-  if (need <= 1 && HALF > 1)
+  // radix-R2 output groups that can hold a displacement in [-maxD, maxD] (lik_window_groups)
+  const int w = bioem::lik_window_groups<BIOEM_N>(maxD);
+  if (w == 1 && HALF > 1)
     return bioem::lik_launch_w<1>(*p, nblocks, s);
   if constexpr (HALF > 2)
-    if (need <= 2)
+    if (w == 2)
       return bioem::lik_launch_w<2>(*p, nblocks, s);
   if constexpr (HALF > 3)
-    if (need <= 3)
+    if (w == 3)
       return bioem::lik_launch_w<3>(*p, nblocks, s);
   if constexpr (HALF > 4)
-    if (need <= 4)
+    if (w == 4)
       return bioem::lik_launch_w<4>(*p, nblocks, s);
   return bioem::lik_launch_w<HALF>(*p, nblocks, s);
 }
