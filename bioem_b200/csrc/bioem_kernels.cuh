@@ -598,6 +598,7 @@ struct LikParams
   float invNN;
   float ex2coef; // (3 - Nt)/2 * log2(e): sum of exp over the window runs in base 2
   double acoef_d;
+  int exp_flags; // timing experiments only (env BIOEM_B200_EXPERIMENT; results are then wrong)
 };
 
 // number of leading (= trailing) radix-R2 output groups that can hold a displacement of
@@ -622,8 +623,11 @@ template <int N> struct LikSmem
   using L = Lay<N>;
   static constexpr int NWARP = NT / 32;
   static constexpr int KC = L::KC;
-  // pass-2 lanes are (k1, c): address k1*ES + c must fall into distinct bank pairs in a half warp
-  static constexpr int ES = L::R2 * KC + ((KC - L::R2 * KC) % 16 + 16) % 16;
+  // Exchange tile E[k1][c][n2] (float2): pass 1 stores with lane = c*R2 + n2 at k1*ES + c*CS + n2
+  // (contiguous per half warp), pass 2 loads with lane = k1*KC + c at the same address for
+  // n2 = 0..R2-1: conflict-free when c*CS == c and k1*ES == k1*KC (mod 16 bank pairs).
+  static constexpr int CS = ((L::R2 - 1 + 15) / 16) * 16 + 1;
+  static constexpr int ES = KC * CS + ((KC - KC * CS) % 16 + 16) % 16;
   static constexpr int YS0 = L::NCOL + ((KC - L::NCOL) % 16 + 16) % 16;
   static constexpr int YS = YS0 > L::NCOL ? YS0 : YS0 + 16; // index NCOL of a row must exist
   static constexpr int EW = L::R1 * ES;                     // float2 per warp
@@ -636,6 +640,14 @@ template <int N> struct LikSmem
 template <int N> __host__ __device__ constexpr size_t lik_smem_bytes(int maxD)
 {
   return LikSmem<N>::bytes(lik_window_groups<N>(maxD));
+}
+
+// 2^x, one MUFU.EX2 (results below the normal range flush to zero)
+__device__ __forceinline__ float ex2_ftz(float x)
+{
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int m)
@@ -684,7 +696,7 @@ template <int N, int W> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)
   using SM = LikSmem<N>;
   constexpr int NK = SM::nk(W); // radix-R2 output groups kept
   constexpr int R1 = L::R1, R2 = L::R2, KC = L::KC, NCOL = L::NCOL, NCH = L::NCH;
-  constexpr int ES = SM::ES, YS = SM::YS, NWARP = SM::NWARP;
+  constexpr int ES = SM::ES, CS = SM::CS, YS = SM::YS, NWARP = SM::NWARP;
   constexpr int NROWS = NK * R1;              // row slots of Y = firstele values per window row
   constexpr int P2 = (KC * R1 + 31) / 32;     // pass-2 trips
   constexpr int CP = NROWS / 2;               // float2 column pairs of a firstele row
@@ -748,9 +760,9 @@ template <int N, int W> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)
 #pragma unroll
   for (int k1 = 1; k1 < R1; k1++)
     tw[k1] = p.tw_inv[a_n2 * R1 + k1];
-  // firstele penalty of this lane's pass-2 outputs: +inf where the raw column index is not a
-  // window displacement (those entries then drop out of the minimum and of the sum)
-  float pen[P2][NK];
+  // bit t*NK + j: output j of this lane's pass-2 item t is a window displacement (the others are
+  // computed and stored too, but never become a minimum and carry +inf into the sum)
+  unsigned vmask = 0;
 #pragma unroll
   for (int t = 0; t < P2; t++)
   {
@@ -758,8 +770,20 @@ template <int N, int W> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)
     const int k1 = (item / KC) % R1;
     bfft::static_for<0, NK>([&](auto j_) {
       constexpr int j = decltype(j_)::value;
-      pen[t][j] = WT[k1 + R1 * k2_of(j)] == 255 ? __int_as_float(0x7f800000) : 0.f;
+      if (WT[k1 + R1 * k2_of(j)] != 255)
+        vmask |= 1u << (t * NK + j);
     });
+  }
+  static_assert(P2 * NK <= 32, "validity mask must fit one register");
+  // +inf for the firstele columns of the exp-sum sweep (tid -> column pair) that are no displacement
+  float colpen0 = 0.f, colpen1 = 0.f;
+  if (tid < RG * CP)
+  {
+    const int col = 2 * (tid % CP);
+    if (WT[col % R1 + R1 * k2_of(col / R1)] == 255)
+      colpen0 = __int_as_float(0x7f800000);
+    if (WT[(col + 1) % R1 + R1 * k2_of((col + 1) / R1)] == 255)
+      colpen1 = __int_as_float(0x7f800000);
   }
 
   const float4 *ref = p.refs + (size_t) m * L::MAP4;
@@ -791,7 +815,7 @@ template <int N, int W> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)
         if (a_act)
         {
           float2 x[R1];
-          const int base = ch * (R1 / 2) * KC * R2 + lane; // == main_idx(ch, 0, a_n2, a_c)
+          const int base = ((p.exp_flags & 1) ? 0 : ch * (R1 / 2) * KC * R2) + lane; // == main_idx(ch, 0, a_n2, a_c)
 #pragma unroll
           for (int n1p = 0; n1p < R1 / 2; n1p++)
           {
@@ -818,7 +842,7 @@ template <int N, int W> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)
             x[k1] = bfft::cmul(x[k1], tw[k1]);
 #pragma unroll
           for (int k1 = 0; k1 < R1; k1++)
-            E[k1 * ES + a_n2 * KC + a_c] = x[k1];
+            E[k1 * ES + a_c * CS + a_n2] = x[k1];
         }
         __syncwarp();
 #pragma unroll
@@ -831,7 +855,7 @@ template <int N, int W> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)
             float2 y[R2];
 #pragma unroll
             for (int n2 = 0; n2 < R2; n2++)
-              y[n2] = E[k1 * ES + n2 * KC + cc];
+              y[n2] = E[k1 * ES + cc * CS + n2];
             bfft::Dft<R2, 1>::run(y);
             float2 *Ycol = Y + k1 * YS + ch * KC + cc;
             bfft::static_for<0, NK>([&](auto j_) {
@@ -885,7 +909,7 @@ template <int N, int W> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)
             x[k1] = bfft::cmul(x[k1], tw[k1]);
 #pragma unroll
           for (int k1 = 0; k1 < R1; k1++)
-            E[k1 * ES + a_n2 * KC + a_c] = x[k1];
+            E[k1 * ES + a_c * CS + a_n2] = x[k1];
         }
         __syncwarp(); // also: every read of this task's Y rows is done, their slots may take FE
 #pragma unroll
@@ -898,7 +922,7 @@ template <int N, int W> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)
             float2 y[R2];
 #pragma unroll
             for (int n2 = 0; n2 < R2; n2++)
-              y[n2] = E[k1 * ES + n2 * KC + cc];
+              y[n2] = E[k1 * ES + cc * CS + n2];
             bfft::Dft<R2, 1>::run(y);
             const int wa = 2 * (p0 + cc);
             const bool vb = wa + 1 < nw;
@@ -914,11 +938,10 @@ template <int N, int W> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)
               fe = __fadd2_rn(fe, __fmul2_rn(make_float2(f_b, f_b), v));
               fe = __fadd2_rn(fe, make_float2(-f_c, -f_c));
               fe = __fadd2_rn(fe, make_float2(-f_d, -f_d));
-              fe = __fadd2_rn(fe, make_float2(pen[t][j], pen[t][j]));
               FEa[j * R1] = fe.x;
               if (vb)
                 FEb[j * R1] = fe.y;
-              if (fe.x <= bfe || (vb && fe.y <= bfe))
+              if (fminf(fe.x, fe.y) <= bfe && ((vmask >> (t * NK + j)) & 1u))
               {
                 // rare: a new per-thread minimum (ties resolved by the enumeration index)
                 const int wy = WT[k1 + R1 * k2_of(j)];
@@ -936,7 +959,7 @@ template <int N, int W> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)
                   bv = v.y;
                 }
               }
-              if (p.dbg_values && pen[t][j] == 0.f)
+              if (p.dbg_values && ((vmask >> (t * NK + j)) & 1u))
               {
                 const int wy = WT[k1 + R1 * k2_of(j)];
                 float *dv = p.dbg_values + ((size_t) oc * p.M + m) * nw * nw;
@@ -974,15 +997,18 @@ template <int N, int W> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)
       {
         const int cpi = tid % CP, rg = tid / CP;
         const float c1 = p.ex2coef, c2 = -0.5f * p.ex2coef, c3 = p.ex2coef * (1.f / 3.f);
+        int slot = RS[rg < nw ? rg : 0];
         for (int wx = rg; wx < nw; wx += RG)
         {
-          const float2 f = reinterpret_cast<const float2 *>(Y + (size_t) RS[wx] * YS)[cpi];
+          float2 f = reinterpret_cast<const float2 *>(Y + (size_t) slot * YS)[cpi];
+          slot = RS[wx + RG < nw ? wx + RG : 0]; // next row's slot, off the critical path
+          f = __fadd2_rn(f, make_float2(colpen0, colpen1));
           // exp(a*log1p(t)), t = (fe - fmin)/fmin >= 0 tiny where it matters; +inf -> 0
           const float2 t = __fmul2_rn(__fadd2_rn(f, make_float2(-fmin, -fmin)), make_float2(inv, inv));
           float2 l = __ffma2_rn(t, make_float2(c3, c3), make_float2(c2, c2));
           l = __ffma2_rn(t, l, make_float2(c1, c1));
           l = __fmul2_rn(t, l);
-          S2 = __fadd2_rn(S2, make_float2(exp2f(l.x), exp2f(l.y)));
+          S2 = __fadd2_rn(S2, make_float2(ex2_ftz(l.x), ex2_ftz(l.y)));
           if (f.x <= fthr || f.y <= fthr)
           {
 #pragma unroll
