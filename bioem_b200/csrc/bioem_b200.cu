@@ -650,7 +650,6 @@ static void fill_lik_params(bioem_b200_context *h, LikParams &lp, int o0, int OB
   lp.invNN = 1.0f / (float) (N * N);
   lp.acoef_d = (double) (3.f - h->cfg.Ntotpi) * 0.5;
   lp.ex2coef = (float) (lp.acoef_d * 1.4426950408889634074);
-  lp.exp_flags = getenv("BIOEM_B200_EXPERIMENT") ? atoi(getenv("BIOEM_B200_EXPERIMENT")) : 0;
 }
 
 int bioem_b200_run(bioem_b200_handle h, int oBegin, int oEnd)

@@ -598,7 +598,6 @@ struct LikParams
   float invNN;
   float ex2coef; // (3 - Nt)/2 * log2(e): sum of exp over the window runs in base 2
   double acoef_d;
-  int exp_flags; // timing experiments only (env BIOEM_B200_EXPERIMENT; results are then wrong)
 };
 
 // number of leading (= trailing) radix-R2 output groups that can hold a displacement of
@@ -658,9 +657,17 @@ __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v,
   return ((unsigned long long) hi << 32) | lo;
 }
 
-constexpr int NCAND = 48; // near-minimum candidates examined exactly per likelihood
+constexpr int NCAND = 8;  // near-minimum candidates examined exactly per likelihood
+constexpr int NPEND = 32; // likelihoods whose double-precision bookkeeping is deferred, then done by 32 lanes at once
 
-// running per-image state of one CTA (kept in shared memory, touched by thread 0 only)
+// monotone map float -> unsigned (a < b  <=>  ord(a) < ord(b))
+__device__ __forceinline__ unsigned float_ordered(float f)
+{
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// running per-image state of one CTA (kept in shared memory, touched by warp 0 only)
 struct BookState
 {
   double Const, Total, anConst, anTotal;
@@ -709,11 +716,14 @@ template <int N, int W> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)
   float2 *Eall = Y + (size_t) NROWS * YS;
   unsigned char *WT = reinterpret_cast<unsigned char *>(Eall + (size_t) NWARP * SM::EW);
   unsigned char *RS = WT + ((N + 15) & ~15);
-  __shared__ unsigned long long s_key[2];
-  __shared__ float s_wsum[2][NWARP];
-  __shared__ float s_winv[2];
-  __shared__ int s_ncand[2];
-  __shared__ uint2 s_cand[2][NCAND];
+  // ring of likelihoods waiting for their bookkeeping: minimum key (firstele bits, enumeration
+  // index), correlation value there, per-warp exp-sums, near-minimum candidates, (o, c) index
+  __shared__ unsigned long long s_pk[NPEND];
+  __shared__ float s_pv[NPEND];
+  __shared__ float s_pws[NPEND][NWARP];
+  __shared__ int s_pnc[NPEND];
+  __shared__ int s_poc[NPEND];
+  __shared__ uint2 s_pcand[NPEND][NCAND];
   __shared__ BookState s_bk;
 
   const int nw = p.nw, nwp = p.nwp;
@@ -737,10 +747,10 @@ template <int N, int W> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)
         RS[nw] = (unsigned char) (j * R1 + k1); // padding row of an odd window: any valid slot
     }
   }
-  if (tid < 2)
+  if (tid < NPEND)
   {
-    s_key[tid] = ~0ull;
-    s_ncand[tid] = 0;
+    s_pk[tid] = ~0ull;
+    s_pnc[tid] = 0;
   }
   if (tid == 0)
   {
@@ -789,7 +799,89 @@ template <int N, int W> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)
   const float4 *ref = p.refs + (size_t) m * L::MAP4;
   const float sR = p.sumRef[m], ssR = p.sumsqRef[m];
   const float Nt = p.Ntotpi;
-  int buf = 0;
+  int slot = 0; // likelihoods in the ring (uniform over the CTA)
+
+  // Bookkeeping of the npend ring entries (bioem_algorithm.h:84-141), by warp 0: lane l takes
+  // entry l -- the two double-precision logs, the exact first-of-ties rule over its near-minimum
+  // candidates -- then the entries are folded in enumeration order semantics: the running maximum
+  // only moves on a strictly greater float-narrowed logpro, so the FIRST maximum wins.
+  auto flush = [&](int npend) {
+    __syncwarp();
+    const bool act = lane < npend;
+    float lpf = __int_as_float(0xff800000), S = 0.f, bvv = 0.f;
+    int lin = 0, oc = 0;
+    ConvParam cpl;
+    cpl.sumC = cpl.sumsqC = 0.f;
+    if (act)
+    {
+      const unsigned long long kmin = s_pk[lane];
+      oc = s_poc[lane];
+      cpl = p.cpar[oc];
+      const float fmin = __uint_as_float((unsigned) (kmin >> 32));
+      lpf = (float) (p.acoef_d * log((double) fmin) + cpl.Bterm);
+      lin = (int) (kmin & 0xffffffffu);
+      const int nc = s_pnc[lane];
+      if (nc <= NCAND)
+        for (int i = 0; i < nc; i++)
+        {
+          const uint2 cd = s_pcand[lane][i];
+          if ((int) cd.y < lin)
+          {
+            const float lc = (float) (p.acoef_d * log((double) __uint_as_float(cd.x)) + cpl.Bterm);
+            if (lc == lpf)
+              lin = (int) cd.y;
+          }
+        }
+#pragma unroll
+      for (int w = 0; w < NWARP; w++)
+        S += s_pws[lane][w];
+      bvv = s_pv[lane];
+    }
+    // arg-max of the batch: greatest lpf, lowest lane (= first in enumeration order) on ties
+    unsigned long long key = ((unsigned long long) float_ordered(lpf) << 32) | (unsigned) (31 - lane);
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1)
+    {
+      const unsigned long long o = shfl_xor_u64(key, sft);
+      key = o > key ? o : key;
+    }
+    const int lbest = 31 - (int) (key & 31u);
+    const float lpfmax = __shfl_sync(0xffffffffu, lpf, lbest);
+    double e = act ? (double) S * exp((double) lpf - (double) lpfmax) : 0.0;
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1)
+      e += __longlong_as_double((long long) shfl_xor_u64((unsigned long long) __double_as_longlong(e), sft));
+    if (lane == lbest)
+    {
+      if (s_bk.Const < (double) lpfmax)
+      {
+        s_bk.Total = s_bk.Total * exp(s_bk.Const - (double) lpfmax) + e;
+        s_bk.Const = (double) lpfmax;
+        s_bk.lpf = lpfmax;
+        s_bk.o = p.o_base + oc / p.C;
+        s_bk.c = oc % p.C;
+        s_bk.lin = lin;
+        s_bk.v = bvv;
+        s_bk.sC = cpl.sumC;
+        s_bk.ssC = cpl.sumsqC;
+      }
+      else
+        s_bk.Total += e * exp((double) lpfmax - s_bk.Const);
+      if (p.angles)
+      {
+        if (s_bk.anConst < (double) lpfmax)
+        {
+          s_bk.anTotal = s_bk.anTotal * exp(s_bk.anConst - (double) lpfmax) + e;
+          s_bk.anConst = (double) lpfmax;
+        }
+        else
+          s_bk.anTotal += e * exp((double) lpfmax - s_bk.anConst);
+      }
+    }
+    s_pk[lane] = ~0ull; // re-arm the ring
+    s_pnc[lane] = 0;
+    __syncwarp();
+  };
 
   for (int ol = o_lo; ol < o_hi; ol++)
   {
@@ -803,6 +895,8 @@ template <int N, int W> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)
       const int oc = ol * p.C + c;
       const float4 *conv = p.convs + (size_t) oc * L::MAP4;
       const ConvParam cp = p.cpar[oc];
+      if (tid == 0)
+        s_poc[slot] = oc;
       // firstele = Nt*(ssR*ssC - v*v) + 2*sR*sC*v - ssR*sC*sC - sR*sR*ssC   (FP32, source order)
       const float f_a = __fmul_rn(ssR, cp.sumsqC);
       const float f_b = __fmul_rn(__fmul_rn(2.f, sR), cp.sumC);
@@ -815,7 +909,7 @@ template <int N, int W> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)
         if (a_act)
         {
           float2 x[R1];
-          const int base = ((p.exp_flags & 1) ? 0 : ch * (R1 / 2) * KC * R2) + lane; // == main_idx(ch, 0, a_n2, a_c)
+          const int base = ch * (R1 / 2) * KC * R2 + lane; // == main_idx(ch, 0, a_n2, a_c)
 #pragma unroll
           for (int n1p = 0; n1p < R1 / 2; n1p++)
           {
@@ -983,12 +1077,12 @@ template <int N, int W> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)
         wbest = o < wbest ? o : wbest;
       }
       if (lane == 0)
-        atomicMin(&s_key[buf], wbest);
+        atomicMin(&s_pk[slot], wbest);
       __syncthreads(); // FE complete, minimum known
-      const unsigned long long kmin = s_key[buf];
+      const unsigned long long kmin = s_pk[slot];
       const float fmin = __uint_as_float((unsigned) (kmin >> 32));
       if (best == kmin)
-        s_winv[buf] = bv;
+        s_pv[slot] = bv;
       // every firstele within NEAR ulps of the minimum may share its float-narrowed logpro
       const float fthr = __uint_as_float((unsigned) (kmin >> 32) + 64u);
       const float inv = __fdiv_rn(1.0f, fmin);
@@ -997,11 +1091,11 @@ template <int N, int W> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)
       {
         const int cpi = tid % CP, rg = tid / CP;
         const float c1 = p.ex2coef, c2 = -0.5f * p.ex2coef, c3 = p.ex2coef * (1.f / 3.f);
-        int slot = RS[rg < nw ? rg : 0];
+        int rsl = RS[rg < nw ? rg : 0];
         for (int wx = rg; wx < nw; wx += RG)
         {
-          float2 f = reinterpret_cast<const float2 *>(Y + (size_t) slot * YS)[cpi];
-          slot = RS[wx + RG < nw ? wx + RG : 0]; // next row's slot, off the critical path
+          float2 f = reinterpret_cast<const float2 *>(Y + (size_t) rsl * YS)[cpi];
+          rsl = RS[wx + RG < nw ? wx + RG : 0]; // next row's slot, off the critical path
           f = __fadd2_rn(f, make_float2(colpen0, colpen1));
           // exp(a*log1p(t)), t = (fe - fmin)/fmin >= 0 tiny where it matters; +inf -> 0
           const float2 t = __fmul2_rn(__fadd2_rn(f, make_float2(-fmin, -fmin)), make_float2(inv, inv));
@@ -1021,9 +1115,9 @@ template <int N, int W> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)
                 const int jj = col / R1, k1 = col % R1;
                 const int k2 = (NK == R2) ? jj : (jj < W ? jj : R2 - NK + jj);
                 const int lin = wx * nw + WT[k1 + R1 * k2];
-                const int slot = atomicAdd(&s_ncand[buf], 1);
-                if (slot < NCAND)
-                  s_cand[buf][slot] = make_uint2(__float_as_uint(fv), (unsigned) lin);
+                const int ci = atomicAdd(&s_pnc[slot], 1);
+                if (ci < NCAND)
+                  s_pcand[slot][ci] = make_uint2(__float_as_uint(fv), (unsigned) lin);
               }
             }
           }
@@ -1034,59 +1128,15 @@ template <int N, int W> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)
       for (int s = 16; s > 0; s >>= 1)
         S += __shfl_xor_sync(0xffffffffu, S, s);
       if (lane == 0)
-        s_wsum[buf][warp] = S;
+        s_pws[slot][warp] = S;
       __syncthreads(); // FE consumed (Y may be overwritten), partial sums and candidates visible
-
-      // ------------------------------------------------ bookkeeping (bioem_algorithm.h:84-141)
-      if (tid == 0)
+      slot++;
+      if (slot == NPEND || (p.angles && c == p.C - 1))
       {
-        float Ssum = 0.f;
-#pragma unroll
-        for (int w = 0; w < NWARP; w++)
-          Ssum += s_wsum[buf][w];
-        const double lp = p.acoef_d * log((double) fmin) + cp.Bterm;
-        const float lpf = (float) lp;
-        int lin = (int) (kmin & 0xffffffffu);
-        const int nc = s_ncand[buf];
-        if (nc <= NCAND)
-          for (int i = 0; i < nc; i++)
-          {
-            const uint2 cd = s_cand[buf][i];
-            if ((int) cd.y < lin)
-            {
-              const float lc = (float) (p.acoef_d * log((double) __uint_as_float(cd.x)) + cp.Bterm);
-              if (lc == lpf)
-                lin = (int) cd.y;
-            }
-          }
-        s_key[buf ^ 1] = ~0ull;
-        s_ncand[buf ^ 1] = 0;
-        if (s_bk.Const < (double) lpf)
-        {
-          s_bk.Total = s_bk.Total * exp(s_bk.Const - (double) lpf) + (double) Ssum;
-          s_bk.Const = (double) lpf;
-          s_bk.lpf = lpf;
-          s_bk.o = p.o_base + ol;
-          s_bk.c = c;
-          s_bk.lin = lin;
-          s_bk.v = s_winv[buf];
-          s_bk.sC = cp.sumC;
-          s_bk.ssC = cp.sumsqC;
-        }
-        else
-          s_bk.Total += (double) Ssum * exp((double) lpf - s_bk.Const);
-        if (p.angles)
-        {
-          if (s_bk.anConst < (double) lpf)
-          {
-            s_bk.anTotal = s_bk.anTotal * exp(s_bk.anConst - (double) lpf) + (double) Ssum;
-            s_bk.anConst = (double) lpf;
-          }
-          else
-            s_bk.anTotal += (double) Ssum * exp((double) lpf - s_bk.anConst);
-        }
+        if (warp == 0)
+          flush(slot);
+        slot = 0;
       }
-      buf ^= 1;
     }
     if (tid == 0 && p.angles)
     {
@@ -1096,6 +1146,8 @@ template <int N, int W> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)
       p.angles[(size_t) (p.o_base + ol) * p.M + m] = a;
     }
   }
+  if (warp == 0 && slot > 0)
+    flush(slot);
   if (tid == 0)
   {
     Running r;
