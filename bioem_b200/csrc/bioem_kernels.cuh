@@ -657,8 +657,10 @@ __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v,
   return ((unsigned long long) hi << 32) | lo;
 }
 
-constexpr int NCAND = 8;  // near-minimum candidates examined exactly per likelihood
 constexpr int NPEND = 32; // likelihoods whose double-precision bookkeeping is deferred, then done by 32 lanes at once
+// sentinels of the running minimum of firstele (real values are many orders of magnitude smaller):
+// outputs that are no window displacement carry FE_INVALID, a thread that has seen nothing FE_NONE
+constexpr float FE_INVALID = 1e36f, FE_NONE = 1e35f;
 
 // monotone map float -> unsigned (a < b  <=>  ord(a) < ord(b))
 __device__ __forceinline__ unsigned float_ordered(float f)
@@ -702,13 +704,10 @@ template <int N, int W> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)
   using L = Lay<N>;
   using SM = LikSmem<N>;
   constexpr int NK = SM::nk(W); // radix-R2 output groups kept
-  constexpr int R1 = L::R1, R2 = L::R2, KC = L::KC, NCOL = L::NCOL, NCH = L::NCH;
+  constexpr int R1 = L::R1, R2 = L::R2, KC = L::KC, NCH = L::NCH;
   constexpr int ES = SM::ES, CS = SM::CS, YS = SM::YS, NWARP = SM::NWARP;
-  constexpr int NROWS = NK * R1;              // row slots of Y = firstele values per window row
-  constexpr int P2 = (KC * R1 + 31) / 32;     // pass-2 trips
-  constexpr int CP = NROWS / 2;               // float2 column pairs of a firstele row
-  constexpr int RG = NT / CP > 0 ? NT / CP : 1; // row groups of the exp-sum sweep
-  static_assert(CP <= NT, "one thread per firstele column pair");
+  constexpr int NROWS = NK * R1;          // row slots of Y
+  constexpr int P2 = (KC * R1 + 31) / 32; // pass-2 trips
   auto k2_of = [](int j) { return (NK == R2) ? j : (j < W ? j : R2 - NK + j); };
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -716,14 +715,14 @@ template <int N, int W> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)
   float2 *Eall = Y + (size_t) NROWS * YS;
   unsigned char *WT = reinterpret_cast<unsigned char *>(Eall + (size_t) NWARP * SM::EW);
   unsigned char *RS = WT + ((N + 15) & ~15);
-  // ring of likelihoods waiting for their bookkeeping: minimum key (firstele bits, enumeration
-  // index), correlation value there, per-warp exp-sums, near-minimum candidates, (o, c) index
-  __shared__ unsigned long long s_pk[NPEND];
-  __shared__ float s_pv[NPEND];
-  __shared__ float s_pws[NPEND][NWARP];
-  __shared__ int s_pnc[NPEND];
+  // ring of likelihoods waiting for their bookkeeping, one entry per warp and likelihood:
+  // minimum key (firstele bits << 32 | enumeration index), runner-up candidate (enumeration index
+  // << 32 | firstele bits), sum of exp relative to the warp minimum, correlation value at the minimum
+  __shared__ unsigned long long s_wk[NPEND][NWARP];
+  __shared__ unsigned long long s_wc[NPEND][NWARP];
+  __shared__ float s_ws[NPEND][NWARP];
+  __shared__ float s_wv[NPEND][NWARP];
   __shared__ int s_poc[NPEND];
-  __shared__ uint2 s_pcand[NPEND][NCAND];
   __shared__ BookState s_bk;
 
   const int nw = p.nw, nwp = p.nwp;
@@ -747,11 +746,6 @@ template <int N, int W> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)
         RS[nw] = (unsigned char) (j * R1 + k1); // padding row of an odd window: any valid slot
     }
   }
-  if (tid < NPEND)
-  {
-    s_pk[tid] = ~0ull;
-    s_pnc[tid] = 0;
-  }
   if (tid == 0)
   {
     s_bk.Const = kMinProb;
@@ -771,7 +765,7 @@ template <int N, int W> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)
   for (int k1 = 1; k1 < R1; k1++)
     tw[k1] = p.tw_inv[a_n2 * R1 + k1];
   // bit t*NK + j: output j of this lane's pass-2 item t is a window displacement (the others are
-  // computed and stored too, but never become a minimum and carry +inf into the sum)
+  // computed too, but enter the minimum / sum as FE_INVALID)
   unsigned vmask = 0;
 #pragma unroll
   for (int t = 0; t < P2; t++)
@@ -785,16 +779,10 @@ template <int N, int W> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)
     });
   }
   static_assert(P2 * NK <= 32, "validity mask must fit one register");
-  // +inf for the firstele columns of the exp-sum sweep (tid -> column pair) that are no displacement
-  float colpen0 = 0.f, colpen1 = 0.f;
-  if (tid < RG * CP)
-  {
-    const int col = 2 * (tid % CP);
-    if (WT[col % R1 + R1 * k2_of(col / R1)] == 255)
-      colpen0 = __int_as_float(0x7f800000);
-    if (WT[(col + 1) % R1 + R1 * k2_of((col + 1) / R1)] == 255)
-      colpen1 = __int_as_float(0x7f800000);
-  }
+  // exp(a*log1p(t)) = 2^(t*(c1 + t*(c2 + t*c3))), a = (3 - Nt)/2, for the tiny t >= 0 that matter;
+  // decreasing in t and 0 for huge t
+  const float c1 = p.ex2coef, c2 = -0.5f * p.ex2coef, c3 = p.ex2coef * (1.f / 3.f);
+  auto expa1p = [&](float t) { return ex2_ftz(t * fmaf(t, fmaf(t, c3, c2), c1)); };
 
   const float4 *ref = p.refs + (size_t) m * L::MAP4;
   const float sR = p.sumRef[m], ssR = p.sumsqRef[m];
@@ -814,28 +802,43 @@ template <int N, int W> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)
     cpl.sumC = cpl.sumsqC = 0.f;
     if (act)
     {
-      const unsigned long long kmin = s_pk[lane];
+      unsigned long long kmin = ~0ull;
+      int wb = 0;
+#pragma unroll
+      for (int w = 0; w < NWARP; w++)
+      {
+        const unsigned long long k = s_wk[lane][w];
+        if (k < kmin)
+        {
+          kmin = k;
+          wb = w;
+        }
+      }
       oc = s_poc[lane];
       cpl = p.cpar[oc];
       const float fmin = __uint_as_float((unsigned) (kmin >> 32));
+      const float inv = __fdiv_rn(1.f, fmin);
       lpf = (float) (p.acoef_d * log((double) fmin) + cpl.Bterm);
       lin = (int) (kmin & 0xffffffffu);
-      const int nc = s_pnc[lane];
-      if (nc <= NCAND)
-        for (int i = 0; i < nc; i++)
-        {
-          const uint2 cd = s_pcand[lane][i];
-          if ((int) cd.y < lin)
-          {
-            const float lc = (float) (p.acoef_d * log((double) __uint_as_float(cd.x)) + cpl.Bterm);
-            if (lc == lpf)
-              lin = (int) cd.y;
-          }
-        }
+      bvv = s_wv[lane][wb];
+      // every firstele within 64 ulps of the minimum may share its float-narrowed logpro; the
+      // reference keeps the FIRST of them in enumeration order (bioem_algorithm.h:84-96)
+      const float fthr = __uint_as_float((unsigned) (kmin >> 32) + 64u);
+      auto consider = [&](float fc, int lc) {
+        if (fc <= fthr && lc < lin)
+          if ((float) (p.acoef_d * log((double) fc) + cpl.Bterm) == lpf)
+            lin = lc;
+      };
 #pragma unroll
       for (int w = 0; w < NWARP; w++)
-        S += s_pws[lane][w];
-      bvv = s_pv[lane];
+      {
+        const unsigned long long k = s_wk[lane][w], cnd = s_wc[lane][w];
+        const float fw = __uint_as_float((unsigned) (k >> 32));
+        S += s_ws[lane][w] * expa1p((fw - fmin) * inv);
+        if (w != wb)
+          consider(fw, (int) (k & 0xffffffffu));
+        consider(__uint_as_float((unsigned) (cnd & 0xffffffffu)), (int) (cnd >> 32));
+      }
     }
     // arg-max of the batch: greatest lpf, lowest lane (= first in enumeration order) on ties
     unsigned long long key = ((unsigned long long) float_ordered(lpf) << 32) | (unsigned) (31 - lane);
@@ -878,8 +881,6 @@ template <int N, int W> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)
           s_bk.anTotal += e * exp((double) lpfmax - s_bk.anConst);
       }
     }
-    s_pk[lane] = ~0ull; // re-arm the ring
-    s_pnc[lane] = 0;
     __syncwarp();
   };
 
@@ -963,8 +964,11 @@ template <int N, int W> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)
       __syncthreads(); // all candidate rows of all columns are in Y
 
       // ------------------------------------------------ row pass (along ky), 2 rows per transform
-      float bfe = __int_as_float(0x7f800000), bv = 0.f;
+      // running minimum of firstele of this thread, its enumeration index and correlation value,
+      // and the sum of exp(logpro - logpro at that minimum) over everything seen so far
+      float bfe = FE_NONE, binv = 1.f / FE_NONE, bv = 0.f;
       int blin = 0x7fffffff;
+      float2 S2 = make_float2(0.f, 0.f);
       const int npairs = nwp / 2;
       for (int p0 = warp * KC; p0 < npairs; p0 += NWARP * KC)
       {
@@ -1020,8 +1024,6 @@ template <int N, int W> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)
             bfft::Dft<R2, 1>::run(y);
             const int wa = 2 * (p0 + cc);
             const bool vb = wa + 1 < nw;
-            float *FEa = reinterpret_cast<float *>(Y + (size_t) RS[wa] * YS) + k1;
-            float *FEb = reinterpret_cast<float *>(Y + (size_t) RS[wa + 1] * YS) + k1;
             bfft::static_for<0, NK>([&](auto j_) {
               constexpr int j = decltype(j_)::value;
               // .x = row wa, .y = row wa + 1
@@ -1032,27 +1034,37 @@ template <int N, int W> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)
               fe = __fadd2_rn(fe, __fmul2_rn(make_float2(f_b, f_b), v));
               fe = __fadd2_rn(fe, make_float2(-f_c, -f_c));
               fe = __fadd2_rn(fe, make_float2(-f_d, -f_d));
-              FEa[j * R1] = fe.x;
-              if (vb)
-                FEb[j * R1] = fe.y;
-              if (fminf(fe.x, fe.y) <= bfe && ((vmask >> (t * NK + j)) & 1u))
+              const bool val = (vmask >> (t * NK + j)) & 1u;
+              fe.x = val ? fe.x : FE_INVALID;
+              fe.y = (val && vb) ? fe.y : FE_INVALID;
+              if (fminf(fe.x, fe.y) <= bfe)
               {
-                // rare: a new per-thread minimum (ties resolved by the enumeration index)
+                // rare: a new minimum of this thread (ties resolved by the enumeration index);
+                // what has been summed so far is re-based onto it
                 const int wy = WT[k1 + R1 * k2_of(j)];
                 const int la = wa * nw + wy, lb = la + nw;
+                const float old = bfe;
                 if (fe.x < bfe || (fe.x == bfe && la < blin))
                 {
                   bfe = fe.x;
                   blin = la;
                   bv = v.x;
                 }
-                if (vb && (fe.y < bfe || (fe.y == bfe && lb < blin)))
+                if (fe.y < bfe || (fe.y == bfe && lb < blin))
                 {
                   bfe = fe.y;
                   blin = lb;
                   bv = v.y;
                 }
+                binv = __fdiv_rn(1.f, bfe);
+                const float sc = expa1p((old - bfe) * binv);
+                S2 = __fmul2_rn(S2, make_float2(sc, sc));
               }
+              float2 tt = __fmul2_rn(__fadd2_rn(fe, make_float2(-bfe, -bfe)), make_float2(binv, binv));
+              float2 ll = __ffma2_rn(tt, make_float2(c3, c3), make_float2(c2, c2));
+              ll = __ffma2_rn(tt, ll, make_float2(c1, c1));
+              ll = __fmul2_rn(tt, ll);
+              S2 = __fadd2_rn(S2, make_float2(ex2_ftz(ll.x), ex2_ftz(ll.y)));
               if (p.dbg_values && ((vmask >> (t * NK + j)) & 1u))
               {
                 const int wy = WT[k1 + R1 * k2_of(j)];
@@ -1067,7 +1079,7 @@ template <int N, int W> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)
         __syncwarp();
       }
 
-      // ------------------------------------------------ minimum over the displacement window
+      // ------------------------------------------------ this warp's share of the window
       const unsigned long long best = ((unsigned long long) __float_as_uint(bfe) << 32) | (unsigned) blin;
       unsigned long long wbest = best;
 #pragma unroll
@@ -1076,60 +1088,28 @@ template <int N, int W> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)
         const unsigned long long o = shfl_xor_u64(wbest, s);
         wbest = o < wbest ? o : wbest;
       }
-      if (lane == 0)
-        atomicMin(&s_pk[slot], wbest);
-      __syncthreads(); // FE complete, minimum known
-      const unsigned long long kmin = s_pk[slot];
-      const float fmin = __uint_as_float((unsigned) (kmin >> 32));
-      if (best == kmin)
-        s_pv[slot] = bv;
-      // every firstele within NEAR ulps of the minimum may share its float-narrowed logpro
-      const float fthr = __uint_as_float((unsigned) (kmin >> 32) + 64u);
-      const float inv = __fdiv_rn(1.0f, fmin);
-      float2 S2 = make_float2(0.f, 0.f);
-      if (tid < RG * CP)
-      {
-        const int cpi = tid % CP, rg = tid / CP;
-        const float c1 = p.ex2coef, c2 = -0.5f * p.ex2coef, c3 = p.ex2coef * (1.f / 3.f);
-        int rsl = RS[rg < nw ? rg : 0];
-        for (int wx = rg; wx < nw; wx += RG)
-        {
-          float2 f = reinterpret_cast<const float2 *>(Y + (size_t) rsl * YS)[cpi];
-          rsl = RS[wx + RG < nw ? wx + RG : 0]; // next row's slot, off the critical path
-          f = __fadd2_rn(f, make_float2(colpen0, colpen1));
-          // exp(a*log1p(t)), t = (fe - fmin)/fmin >= 0 tiny where it matters; +inf -> 0
-          const float2 t = __fmul2_rn(__fadd2_rn(f, make_float2(-fmin, -fmin)), make_float2(inv, inv));
-          float2 l = __ffma2_rn(t, make_float2(c3, c3), make_float2(c2, c2));
-          l = __ffma2_rn(t, l, make_float2(c1, c1));
-          l = __fmul2_rn(t, l);
-          S2 = __fadd2_rn(S2, make_float2(ex2_ftz(l.x), ex2_ftz(l.y)));
-          if (f.x <= fthr || f.y <= fthr)
-          {
-#pragma unroll
-            for (int e = 0; e < 2; e++)
-            {
-              const float fv = e ? f.y : f.x;
-              if (fv <= fthr)
-              {
-                const int col = 2 * cpi + e;
-                const int jj = col / R1, k1 = col % R1;
-                const int k2 = (NK == R2) ? jj : (jj < W ? jj : R2 - NK + jj);
-                const int lin = wx * nw + WT[k1 + R1 * k2];
-                const int ci = atomicAdd(&s_pnc[slot], 1);
-                if (ci < NCAND)
-                  s_pcand[slot][ci] = make_uint2(__float_as_uint(fv), (unsigned) lin);
-              }
-            }
-          }
-        }
-      }
-      float S = S2.x + S2.y;
+      const float fw = __uint_as_float((unsigned) (wbest >> 32));
+      float S = (S2.x + S2.y) * expa1p((bfe - fw) * __fdiv_rn(1.f, fw));
+      // runner-up: the lowest enumeration index among the other threads' minima within 64 ulps
+      unsigned long long cand = ~0ull;
+      if (best != wbest && bfe <= __uint_as_float((unsigned) (wbest >> 32) + 64u))
+        cand = ((unsigned long long) (unsigned) blin << 32) | __float_as_uint(bfe);
 #pragma unroll
       for (int s = 16; s > 0; s >>= 1)
+      {
         S += __shfl_xor_sync(0xffffffffu, S, s);
+        const unsigned long long o = shfl_xor_u64(cand, s);
+        cand = o < cand ? o : cand;
+      }
+      if (best == wbest)
+        s_wv[slot][warp] = bv;
       if (lane == 0)
-        s_pws[slot][warp] = S;
-      __syncthreads(); // FE consumed (Y may be overwritten), partial sums and candidates visible
+      {
+        s_wk[slot][warp] = wbest;
+        s_wc[slot][warp] = cand;
+        s_ws[slot][warp] = S;
+      }
+      __syncthreads(); // Y consumed (the next column pass may overwrite it), ring entry complete
       slot++;
       if (slot == NPEND || (p.angles && c == p.C - 1))
       {
