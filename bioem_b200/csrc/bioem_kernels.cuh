@@ -796,7 +796,7 @@ template <int N, int W> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)
   auto flush = [&](int npend) {
     __syncwarp();
     const bool act = lane < npend;
-    float lpf = __int_as_float(0xff800000), S = 0.f, bvv = 0.f;
+    float lpf = __int_as_float(0xff800000), S = 0.f, bvv = 0.f, fminl = 1.f;
     int lin = 0, oc = 0;
     ConvParam cpl;
     cpl.sumC = cpl.sumsqC = 0.f;
@@ -818,26 +818,54 @@ template <int N, int W> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)
       cpl = p.cpar[oc];
       const float fmin = __uint_as_float((unsigned) (kmin >> 32));
       const float inv = __fdiv_rn(1.f, fmin);
+      fminl = fmin;
       lpf = (float) (p.acoef_d * log((double) fmin) + cpl.Bterm);
       lin = (int) (kmin & 0xffffffffu);
       bvv = s_wv[lane][wb];
-      // every firstele within 64 ulps of the minimum may share its float-narrowed logpro; the
-      // reference keeps the FIRST of them in enumeration order (bioem_algorithm.h:84-96)
-      const float fthr = __uint_as_float((unsigned) (kmin >> 32) + 64u);
-      auto consider = [&](float fc, int lc) {
-        if (fc <= fthr && lc < lin)
-          if ((float) (p.acoef_d * log((double) fc) + cpl.Bterm) == lpf)
-            lin = lc;
-      };
-#pragma unroll
+#pragma unroll 1
       for (int w = 0; w < NWARP; w++)
       {
-        const unsigned long long k = s_wk[lane][w], cnd = s_wc[lane][w];
-        const float fw = __uint_as_float((unsigned) (k >> 32));
+        const float fw = __uint_as_float((unsigned) (s_wk[lane][w] >> 32));
         S += s_ws[lane][w] * expa1p((fw - fmin) * inv);
-        if (w != wb)
-          consider(fw, (int) (k & 0xffffffffu));
-        consider(__uint_as_float((unsigned) (cnd & 0xffffffffu)), (int) (cnd >> 32));
+      }
+    }
+    // Every firstele within 64 ulps of the minimum may share its float-narrowed logpro; the
+    // reference keeps the FIRST of them in enumeration order (bioem_algorithm.h:84-96).  The warps'
+    // minima and runner-ups with a lower enumeration index are examined exactly, lowest index
+    // first (warp-uniform loop: a round costs one double-precision log, and rounds are rare).
+    int tried = -1; // candidates up to this enumeration index have been examined
+#pragma unroll 1
+    for (int round = 0; round < 4; round++)
+    {
+      int lc = 0x7fffffff;
+      float fc = 0.f;
+      if (act)
+      {
+        const float fthr = __uint_as_float(__float_as_uint(fminl) + 64u);
+#pragma unroll 1
+        for (int w = 0; w < 2 * NWARP; w++)
+        {
+          const unsigned long long k = (w < NWARP) ? s_wk[lane][w] : s_wc[lane][w - NWARP];
+          // minima carry (firstele bits << 32 | index), runner-ups (index << 32 | firstele bits)
+          const int l = (w < NWARP) ? (int) (k & 0xffffffffu) : (int) (k >> 32);
+          const float f = __uint_as_float((w < NWARP) ? (unsigned) (k >> 32) : (unsigned) (k & 0xffffffffu));
+          if (k != ~0ull && f <= fthr && l < lin && l > tried && l < lc)
+          {
+            lc = l;
+            fc = f;
+          }
+        }
+      }
+      if (__ballot_sync(0xffffffffu, lc != 0x7fffffff) == 0u)
+        break;
+      if (lc != 0x7fffffff)
+      {
+        tried = lc;
+        if ((float) (p.acoef_d * log((double) fc) + cpl.Bterm) == lpf)
+        {
+          lin = lc;
+          tried = 0x7ffffffe; // done: nothing with a lower index is left
+        }
       }
     }
     // arg-max of the batch: greatest lpf, lowest lane (= first in enumeration order) on ties
