@@ -67,9 +67,11 @@ def lib():
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = _build.LIB
-    if not os.path.exists(path) or (os.path.exists(_build.NVCC) and _build.needs_build()):
-        path = _build.build()
+    path = os.environ.get("BIOEM_B200_LIB")  # an alternative build of the same library (experiments)
+    if not path:
+        path = _build.LIB
+        if not os.path.exists(path) or (os.path.exists(_build.NVCC) and _build.needs_build()):
+            path = _build.build()
     if not os.path.exists(path):
         raise BioemError(f"{path} is missing and cannot be built: the CUDA extension is required "
                          "(there is no CPU fallback)")

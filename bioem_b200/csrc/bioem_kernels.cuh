@@ -617,10 +617,38 @@ template <int N> __host__ __device__ constexpr int lik_window_groups(int maxD)
 //       (FE, NK*R1 floats per window row).
 //   E   per warp [R1][ES] float2: the exchange tile between the two radix passes
 //   WT  [N] window table, RS [256] window row -> row slot
+// warps per CTA of the fused kernel.  Measured on B200 at N = 224 (tools/build_variant.py):
+// 8 warps 55.1 ns/likelihood, 7 warps (which would divide both the 56 column chunks and the 21
+// row tasks evenly) 58.1 ns -- registers are granted in units of 4 warps, so 7 warps buy nothing.
+template <int N> __host__ __device__ constexpr int lik_warps()
+{
+#ifdef BIOEM_LW
+  return BIOEM_LW;
+#else
+  return 8;
+#endif
+}
+// float4 operand pairs of the next column chunk that are loaded one chunk ahead (the rest is
+// loaded when the chunk starts).  Bounded by the 128-register budget of two CTAs per SM: measured
+// at N = 224, 2 pairs ahead 54.9 ns (no gain), 4 pairs 61.5 ns (spills), so the default is none.
+template <int N> __host__ __device__ constexpr int lik_prefetch()
+{
+#ifdef BIOEM_PF
+  return BIOEM_PF < Lay<N>::R1 / 2 ? BIOEM_PF : Lay<N>::R1 / 2;
+#else
+  return 0;
+#endif
+}
+
 template <int N> struct LikSmem
 {
   using L = Lay<N>;
-  static constexpr int NWARP = NT / 32;
+  static constexpr int NWARP = lik_warps<N>();
+  static constexpr int LNT = 32 * NWARP; // threads per CTA
+  // registers per thread: two CTAs per SM up to N = 224 (registers are granted to a CTA in units
+  // of 4 warps, so 7 warps cost as many as 8), one CTA per SM above (the row slots then need
+  // more than half of the shared memory anyway)
+  static constexpr int MAXREG = N <= 224 ? 128 : 255;
   static constexpr int KC = L::KC;
   // Exchange tile E[k1][c][n2] (float2): pass 1 stores with lane = c*R2 + n2 at k1*ES + c*CS + n2
   // (contiguous per half warp), pass 2 loads with lane = k1*KC + c at the same address for
@@ -699,7 +727,8 @@ struct BookState
 // All butterflies run on packed FP32x2 instructions.  Three CTA-wide barriers per
 // likelihood; no correlation map ever leaves the SM.
 // ===========================================================================
-template <int N, int W> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)) likelihood_kernel(LikParams p)
+template <int N, int W>
+__global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXREG) likelihood_kernel(LikParams p)
 {
   using L = Lay<N>;
   using SM = LikSmem<N>;
@@ -733,7 +762,7 @@ template <int N, int W> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)
   const int o_lo = g * p.OG;
   const int o_hi = min(p.OBcur, o_lo + p.OG);
 
-  for (int i = tid; i < N; i += NT)
+  for (int i = tid; i < N; i += SM::LNT)
   {
     const unsigned w = p.wtab[i];
     WT[i] = (unsigned char) w;
@@ -912,6 +941,23 @@ template <int N, int W> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)
     __syncwarp();
   };
 
+  // Operands of the column chunk in flight: the loads of a warp's NEXT chunk are issued before the
+  // second radix pass of the current one (and those of the next likelihood's first chunk before
+  // the closing barrier), so that the L2 latency is covered by a whole chunk of work.
+  constexpr int PF = lik_prefetch<N>();
+  float4 Rq[PF > 0 ? PF : 1], Vq[PF > 0 ? PF : 1];
+  auto fetch = [&](int chn, const float4 *cv) {
+    const int base = chn * (R1 / 2) * KC * R2 + lane; // == main_idx(chn, 0, a_n2, a_c)
+#pragma unroll
+    for (int n1p = 0; n1p < PF; n1p++)
+    {
+      Rq[n1p] = ldg4(ref + base + n1p * KC * R2);
+      Vq[n1p] = ldg4(cv + base + n1p * KC * R2);
+    }
+  };
+  if (PF > 0 && a_act && warp < NCH && o_lo < o_hi)
+    fetch(warp, p.convs + (size_t) o_lo * p.C * L::MAP4);
+
   for (int ol = o_lo; ol < o_hi; ol++)
   {
     if (tid == 0)
@@ -938,12 +984,13 @@ template <int N, int W> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)
         if (a_act)
         {
           float2 x[R1];
+#pragma unroll
           const int base = ch * (R1 / 2) * KC * R2 + lane; // == main_idx(ch, 0, a_n2, a_c)
 #pragma unroll
           for (int n1p = 0; n1p < R1 / 2; n1p++)
           {
-            const float4 r = ldg4(ref + base + n1p * KC * R2);
-            const float4 v = ldg4(conv + base + n1p * KC * R2);
+            const float4 r = n1p < PF ? Rq[n1p] : ldg4(ref + base + n1p * KC * R2);
+            const float4 v = n1p < PF ? Vq[n1p] : ldg4(conv + base + n1p * KC * R2);
             x[2 * n1p] = bfft::cmulc(make_float2(v.x, v.y), make_float2(r.x, r.y));
             x[2 * n1p + 1] = bfft::cmulc(make_float2(v.z, v.w), make_float2(r.z, r.w));
           }
@@ -968,6 +1015,8 @@ template <int N, int W> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)
             E[k1 * ES + a_c * CS + a_n2] = x[k1];
         }
         __syncwarp();
+        if (PF > 0 && a_act && ch + NWARP < NCH)
+          fetch(ch + NWARP, conv);
 #pragma unroll
         for (int t = 0; t < P2; t++)
         {
@@ -1137,6 +1186,8 @@ template <int N, int W> __global__ void __launch_bounds__(NT, (N <= 256 ? 2 : 1)
         s_wc[slot][warp] = cand;
         s_ws[slot][warp] = S;
       }
+      if (PF > 0 && a_act && warp < NCH && oc + 1 < o_hi * p.C)
+        fetch(warp, conv + L::MAP4); // first chunk of the next likelihood (next conv spectrum of the batch)
       __syncthreads(); // Y consumed (the next column pass may overwrite it), ring entry complete
       slot++;
       if (slot == NPEND || (p.angles && c == p.C - 1))

@@ -12,7 +12,7 @@ template <int W> static cudaError_t lik_launch_w(const LikParams &p, int nblocks
   cudaError_t e = cudaFuncSetAttribute(likelihood_kernel<BIOEM_N, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
   if (e != cudaSuccess)
     return e;
-  likelihood_kernel<BIOEM_N, W><<<nblocks, NT, smem, s>>>(p);
+  likelihood_kernel<BIOEM_N, W><<<nblocks, LikSmem<BIOEM_N>::LNT, smem, s>>>(p);
   return cudaGetLastError();
 }
 } // namespace bioem
