@@ -92,3 +92,111 @@ def test_final_logprob_and_merge_host():
     np.testing.assert_allclose(merged["Total"], full["Total"], rtol=1e-12)
     for k in ("Constoadd", "cent_x", "cent_y", "orient", "conv", "norm", "mu"):
         np.testing.assert_array_equal(merged[k], full[k])
+
+
+# ---------------------------------------------------------------------------------------------
+# bioEM_b200: the reference's command line / file formats on top of the C ABI.
+# Without a GPU only the front end can run: BIOEM_B200_DUMP_INPUTS makes the binary write what it
+# would upload and stop before any device work.
+HOST_BIN = os.path.join(ROOT, "bioem_b200", "bin", "bioEM_b200")
+
+
+def _build_host_bin():
+    import subprocess
+    api.lib()
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "bioem_b200", "csrc", "host")],
+                          stdout=subprocess.DEVNULL)
+    return HOST_BIN
+
+
+@pytest.mark.parametrize("name", ["toy32", "toy36g2", "toy64"])
+def test_host_binary_reads_the_reference_formats(name, tmp_path):
+    """Parameter file, fixed-width orientation list, text model, text / MRC particle stacks: the
+    C++ front end must hand the library exactly the arrays the Python mirror builds (bit for bit;
+    the mirror itself is pinned to the oracle in test_host_preparation_matches_oracle)."""
+    import subprocess
+    from bioem_b200.cases import reference_cli
+    exe = _build_host_bin()
+    cd = build_case(name, str(tmp_path))
+    dump = tmp_path / "dump"
+    dump.mkdir()
+    r = subprocess.run([exe] + reference_cli(cd), cwd=tmp_path, capture_output=True, text=True,
+                       env={**os.environ, "BIOEM_B200_DUMP_INPUTS": str(dump)})
+    assert r.returncode == 0, r.stdout[-500:] + r.stderr[-500:]
+    hi, parts = api.inputs_for_case(cd)
+    pts = np.fromfile(dump / "points.bin", dtype=api.MODEL_POINT_DTYPE)
+    assert pts.tobytes() == hi.points.tobytes()
+    assert np.array_equal(np.fromfile(dump / "maps.bin", dtype=np.float32).reshape(parts.shape), parts)
+    assert np.array_equal(np.fromfile(dump / "angles.bin", dtype=np.float32).reshape(-1, 4), hi.angles)
+    assert np.array_equal(np.fromfile(dump / "ctfparam.bin", dtype=np.float32).reshape(-1, 4), hi.CtfParam)
+    assert np.array_equal(np.fromfile(dump / "refctf.bin", dtype=np.float32).reshape(hi.refCTF.shape), hi.refCTF)
+    meta = dict(ln.split() for ln in open(dump / "meta.txt"))
+    assert np.float32(meta["volu"]) == np.float32(hi.cfg.volu)
+    assert np.float32(meta["NormDen"]) == np.float32(hi.NormDen)
+    assert int(meta["O"]) == hi.O and int(meta["C"]) == hi.C and int(meta["M"]) == parts.shape[0]
+
+
+def test_host_binary_orientation_grids_and_errors(tmp_path):
+    """Euler / quaternion grid generators (reference param.cpp:1009-1048,1141-1210) and the
+    reference's fatal input errors (exit code 1)."""
+    import subprocess
+    from bioem_b200 import synth
+    exe = _build_host_bin()
+    cd = build_case("toy32", str(tmp_path))
+    base = ["--Modelfile", cd.paths["model"], "--Particlesfile", cd.paths["particles"]]
+
+    def run(param_text, extra=()):
+        pf = tmp_path / "p.txt"
+        pf.write_text(param_text)
+        dump = tmp_path / "d"
+        dump.mkdir(exist_ok=True)
+        return subprocess.run([exe] + base + ["--Inputfile", str(pf)] + list(extra), cwd=tmp_path,
+                              capture_output=True, text=True,
+                              env={**os.environ, "BIOEM_B200_DUMP_INPUTS": str(dump)}), dump
+
+    common = ("PIXEL_SIZE 1.5\nNUMBER_PIXELS 32\nDISPLACE_CENTER 4 1\nCTF_DEFOCUS 1.0 4.0 3\n"
+              "CTF_B_ENV 2.0 300.0 1\nCTF_AMPLITUDE 0.1 0.1 1\n")
+    # Euler grid: nAlpha * nBeta * nAlpha orientations, cell centres
+    r, dump = run(common + "GRIDPOINTS_ALPHA 4\nGRIDPOINTS_BETA 3\n")
+    assert r.returncode == 0, r.stderr
+    ang = np.fromfile(dump / "angles.bin", dtype=np.float32).reshape(-1, 4)
+    assert ang.shape[0] == 4 * 3 * 4
+    ga = np.float32(2 * np.pi / 4)
+    assert abs(ang[0, 0] - (-np.pi + ga / 2)) < 1e-6 and abs(ang[0, 1] - np.arccos(-1 + 1 / 3)) < 1e-6
+    assert np.all(ang[:, 3] == 0)
+    # quaternion grid: both signs of q4, unit norm
+    r, dump = run(common + "USE_QUATERNIONS\nGRIDPOINTS_QUATERNION 3\n")
+    assert r.returncode == 0, r.stderr
+    q = np.fromfile(dump / "angles.bin", dtype=np.float32).reshape(-1, 4)
+    assert q.shape[0] % 2 == 0 and q.shape[0] > 0
+    np.testing.assert_allclose((q.astype(np.float64) ** 2).sum(1), 1.0, atol=1e-6)
+    assert np.array_equal(q[0::2, :3], q[1::2, :3]) and np.array_equal(q[0::2, 3], -q[1::2, 3])
+    # fatal errors of the reference
+    r, _ = run(common.replace("PIXEL_SIZE 1.5\n", "") + "GRIDPOINTS_ALPHA 4\nGRIDPOINTS_BETA 3\n")
+    assert r.returncode == 1 and "PIXEL_SIZE" in r.stderr
+    r, _ = run(common)
+    assert r.returncode == 1 and "GRIDPOINTS_ALPHA" in r.stderr
+    r, _ = run(common.replace("CTF_DEFOCUS 1.0 4.0 3", "CTF_DEFOCUS 1.0 9.0 3") + "GRIDPOINTS_ALPHA 4\nGRIDPOINTS_BETA 3\n")
+    assert r.returncode == 1 and "8micro-m" in r.stderr
+    r = subprocess.run([exe, "--Modelfile", "x"], capture_output=True, text=True)
+    assert r.returncode == 1
+    r = subprocess.run([exe] + base + ["--Inputfile", "p.txt", "--ReadMultipleMRC"], cwd=tmp_path,
+                       capture_output=True, text=True)
+    assert r.returncode == 1 and "--ReadMRC" in r.stderr
+    # PDB reader: CA atoms only, residue tables
+    pdb = tmp_path / "m.pdb"
+    pdb.write_text("ATOM      1  N   GLY A   1      11.104  13.207   2.100  1.00  0.00\n"
+                   "ATOM      2  CA  GLY A   1      12.000  14.000   3.000  1.00  0.00\n"
+                   "ATOM      3  CA  TRP A   2      -2.000   4.000  -6.000  1.00  0.00\n"
+                   "HETATM    4  CA  XXX A   3       0.000   0.000   0.000  1.00  0.00\n")
+    pf = tmp_path / "p.txt"
+    pf.write_text(common + "GRIDPOINTS_ALPHA 4\nGRIDPOINTS_BETA 3\nNO_CENTEROFMASS\n")
+    dump = tmp_path / "d"
+    r = subprocess.run([exe, "--Modelfile", str(pdb), "--ReadPDB", "--Particlesfile", cd.paths["particles"],
+                        "--Inputfile", str(pf)], cwd=tmp_path, capture_output=True, text=True,
+                       env={**os.environ, "BIOEM_B200_DUMP_INPUTS": str(dump)})
+    assert r.returncode == 0, r.stderr
+    pts = np.fromfile(dump / "points.bin", dtype=api.MODEL_POINT_DTYPE)
+    assert len(pts) == 2
+    assert np.allclose(pts["pos"], [[12, 14, 3], [-2, 4, -6]])
+    assert np.allclose(pts["radius"], [2.25, 3.4]) and np.allclose(pts["density"], [40, 108])
