@@ -44,6 +44,15 @@ WORKLOADS = {
 }
 
 
+def _traffic(kernel: str):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture (or None)."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        return int(json.load(open(p))[kernel]["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -235,7 +244,8 @@ def run_ours(args):
             ach = per_rank_lik * 8.0 * F / (lik_ms / 1e3) / 1e9
             flop = 2.5 * N * N * np.log2(N * N)
             roof = {"bound": "hbm", "achieved": round(ach, 1), "peak": hbm_peak, "unit": "GB/s",
-                    "frac": round(ach / hbm_peak, 4), "traffic": None, "peak_source": peak_src,
+                    "frac": round(ach / hbm_peak, 4), "traffic": _traffic(f"likelihood_kernel<{N}>"),
+                    "peak_source": peak_src,
                     "kernel": f"likelihood_kernel<{N}>", "launches": lik_launches,
                     "avg_launch_ms": round(lik_ms / lik_launches, 3),
                     "algorithmic_bytes_per_likelihood": 8 * F,
