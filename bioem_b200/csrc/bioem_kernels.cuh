@@ -625,7 +625,9 @@ template <int N> __host__ __device__ constexpr int lik_warps()
 #ifdef BIOEM_LW
   return BIOEM_LW;
 #else
-  return 8;
+  // above N = 224 one CTA fills the SM (its row slots need more than half of the shared memory):
+  // 12 warps of 168 registers instead of 8 (N = 360: 248.7 -> see profiles ns/likelihood)
+  return N > 224 ? 12 : 8;
 #endif
 }
 // float4 operand pairs of the next column chunk that are loaded one chunk ahead (the rest is
@@ -648,7 +650,7 @@ template <int N> struct LikSmem
   // registers per thread: two CTAs per SM up to N = 224 (registers are granted to a CTA in units
   // of 4 warps, so 7 warps cost as many as 8), one CTA per SM above (the row slots then need
   // more than half of the shared memory anyway)
-  static constexpr int MAXREG = N <= 224 ? 128 : 255;
+  static constexpr int MAXREG = N <= 224 ? 128 : (65536 / LNT) / 8 * 8 > 255 ? 255 : (65536 / LNT) / 8 * 8;
   static constexpr int KC = L::KC;
   // Exchange tile E[k1][c][n2] (float2): pass 1 stores with lane = c*R2 + n2 at k1*ES + c*CS + n2
   // (contiguous per half warp), pass 2 loads with lane = k1*KC + c at the same address for
@@ -685,7 +687,9 @@ __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v,
   return ((unsigned long long) hi << 32) | lo;
 }
 
-constexpr int NPEND = 32; // likelihoods whose double-precision bookkeeping is deferred, then done by 32 lanes at once
+// likelihoods whose double-precision bookkeeping is deferred, then done by up to 32 lanes at once
+// (16 where a single 12-warp CTA already needs nearly all of the shared memory)
+template <int N> __host__ __device__ constexpr int lik_pending() { return N > 224 ? 16 : 32; }
 // sentinels of the running minimum of firstele (real values are many orders of magnitude smaller):
 // outputs that are no window displacement carry FE_INVALID, a thread that has seen nothing FE_NONE
 constexpr float FE_INVALID = 1e36f, FE_NONE = 1e35f;
@@ -737,6 +741,7 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
   constexpr int ES = SM::ES, CS = SM::CS, YS = SM::YS, NWARP = SM::NWARP;
   constexpr int NROWS = NK * R1;          // row slots of Y
   constexpr int P2 = (KC * R1 + 31) / 32; // pass-2 trips
+  constexpr int NPEND = lik_pending<N>();
   auto k2_of = [](int j) { return (NK == R2) ? j : (j < W ? j : R2 - NK + j); };
 
   extern __shared__ __align__(16) unsigned char smem_raw[];

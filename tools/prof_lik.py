@@ -11,7 +11,8 @@ from bioem_b200.cases import build_case  # noqa: E402
 
 name = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
 n_or = int(sys.argv[2]) if len(sys.argv) > 2 else 45
-cd = build_case(name)
+n_part = int(sys.argv[3]) if len(sys.argv) > 3 else None
+cd = build_case(name, n_particles=n_part, n_orient=n_or if n_part else None)
 hi, parts = api.inputs_for_case(cd)
 eng = api.Engine(hi.cfg, 0)
 eng.upload_all(hi, parts)
