@@ -617,17 +617,50 @@ template <int N> __host__ __device__ constexpr int lik_window_groups(int maxD)
 //       (FE, NK*R1 floats per window row).
 //   E   per warp [R1][ES] float2: the exchange tile between the two radix passes
 //   WT  [N] window table, RS [256] window row -> row slot
-// warps per CTA of the fused kernel.  Measured on B200 at N = 224 (tools/build_variant.py):
-// 8 warps 55.1 ns/likelihood, 7 warps (which would divide both the 56 column chunks and the 21
-// row tasks evenly) 58.1 ns -- registers are granted in units of 4 warps, so 7 warps buy nothing.
+// Shared-memory geometry of the fused kernel (see LikSmem below) as free functions, so that the
+// warp count can be chosen from it.
+template <int N> struct LikGeo
+{
+  using L = Lay<N>;
+  static constexpr int KC = L::KC;
+  // Exchange tile E[k1][c][n2] (float2): pass 1 stores with lane = c*R2 + n2 at k1*ES + c*CS + n2
+  // (contiguous per half warp), pass 2 loads with lane = k1*KC + c at the same address for
+  // n2 = 0..R2-1: conflict-free when c*CS == c and k1*ES == k1*KC (mod 16 bank pairs).
+  static constexpr int CS = ((L::R2 - 1 + 15) / 16) * 16 + 1;
+  static constexpr int ES = KC * CS + ((KC - KC * CS) % 16 + 16) % 16;
+  static constexpr int YS0 = L::NCOL + ((KC - L::NCOL) % 16 + 16) % 16;
+  static constexpr int YS = YS0 > L::NCOL ? YS0 : YS0 + 16; // index NCOL of a row must exist
+  static constexpr int EW = L::R1 * ES;                     // float2 per warp
+  __host__ __device__ static constexpr int nk(int W) { return 2 * W >= L::R2 ? L::R2 : 2 * W; }
+  __host__ __device__ static constexpr size_t dyn_bytes(int W, int nwarp)
+  {
+    return ((size_t) nk(W) * L::R1 * YS + (size_t) nwarp * EW) * sizeof(float2) + ((N + 15) & ~15) + 256;
+  }
+};
+template <int N> __host__ __device__ constexpr int lik_window_groups(int maxD);
+
+// likelihoods whose double-precision bookkeeping is deferred, then done by up to 32 lanes at once
+// (16 where a single CTA already needs nearly all of the shared memory)
+template <int N> __host__ __device__ constexpr int lik_pending() { return N > 224 ? 16 : 32; }
+
+// warps per CTA of the fused kernel.  Up to N = 224 two CTAs of 8 warps share an SM.  Measured
+// on B200 at N = 224 (tools/build_variant.py): 8 warps 55.1 ns/likelihood, 7 warps (which would
+// divide both the 56 column chunks and the 21 row tasks evenly) 58.1 ns -- registers are granted
+// in units of 4 warps, so 7 warps buy nothing.  Above, one CTA fills the SM (its row slots need
+// more than half of the shared memory): as many warps (12, 10 or 8) as fit next to the row slots
+// of the production window DISPLACE_CENTER 40 (N = 360: 8 warps 248.7, 12 warps 204.7 ns).
 template <int N> __host__ __device__ constexpr int lik_warps()
 {
 #ifdef BIOEM_LW
   return BIOEM_LW;
 #else
-  // above N = 224 one CTA fills the SM (its row slots need more than half of the shared memory):
-  // 12 warps of 168 registers instead of 8 (N = 360: 248.7 -> see profiles ns/likelihood)
-  return N > 224 ? 12 : 8;
+  if (N <= 224)
+    return 8;
+  constexpr size_t budget = 227 * 1024 - 1024;
+  for (int nw = 12; nw > 8; nw -= 2)
+    if (LikGeo<N>::dyn_bytes(lik_window_groups<N>(40), nw) + (size_t) lik_pending<N>() * nw * 24 + 256 <= budget)
+      return nw;
+  return 8;
 #endif
 }
 // float4 operand pairs of the next column chunk that are loaded one chunk ahead (the rest is
@@ -645,26 +678,15 @@ template <int N> __host__ __device__ constexpr int lik_prefetch()
 template <int N> struct LikSmem
 {
   using L = Lay<N>;
+  using G = LikGeo<N>;
   static constexpr int NWARP = lik_warps<N>();
   static constexpr int LNT = 32 * NWARP; // threads per CTA
   // registers per thread: two CTAs per SM up to N = 224 (registers are granted to a CTA in units
-  // of 4 warps, so 7 warps cost as many as 8), one CTA per SM above (the row slots then need
-  // more than half of the shared memory anyway)
-  static constexpr int MAXREG = N <= 224 ? 128 : (65536 / LNT) / 8 * 8 > 255 ? 255 : (65536 / LNT) / 8 * 8;
-  static constexpr int KC = L::KC;
-  // Exchange tile E[k1][c][n2] (float2): pass 1 stores with lane = c*R2 + n2 at k1*ES + c*CS + n2
-  // (contiguous per half warp), pass 2 loads with lane = k1*KC + c at the same address for
-  // n2 = 0..R2-1: conflict-free when c*CS == c and k1*ES == k1*KC (mod 16 bank pairs).
-  static constexpr int CS = ((L::R2 - 1 + 15) / 16) * 16 + 1;
-  static constexpr int ES = KC * CS + ((KC - KC * CS) % 16 + 16) % 16;
-  static constexpr int YS0 = L::NCOL + ((KC - L::NCOL) % 16 + 16) % 16;
-  static constexpr int YS = YS0 > L::NCOL ? YS0 : YS0 + 16; // index NCOL of a row must exist
-  static constexpr int EW = L::R1 * ES;                     // float2 per warp
-  __host__ __device__ static constexpr int nk(int W) { return 2 * W >= L::R2 ? L::R2 : 2 * W; }
-  __host__ __device__ static constexpr size_t bytes(int W)
-  {
-    return ((size_t) nk(W) * L::R1 * YS + (size_t) NWARP * EW) * sizeof(float2) + ((N + 15) & ~15) + 256;
-  }
+  // of 4 warps, so 7 warps cost as many as 8), one CTA per SM above
+  static constexpr int MAXREG = N <= 224 ? 128 : (65536 / (32 * ((NWARP + 3) / 4 * 4))) / 8 * 8 > 255 ? 255 : (65536 / (32 * ((NWARP + 3) / 4 * 4))) / 8 * 8;
+  static constexpr int KC = G::KC, CS = G::CS, ES = G::ES, YS = G::YS, EW = G::EW;
+  __host__ __device__ static constexpr int nk(int W) { return G::nk(W); }
+  __host__ __device__ static constexpr size_t bytes(int W) { return G::dyn_bytes(W, NWARP); }
 };
 template <int N> __host__ __device__ constexpr size_t lik_smem_bytes(int maxD)
 {
@@ -687,9 +709,6 @@ __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v,
   return ((unsigned long long) hi << 32) | lo;
 }
 
-// likelihoods whose double-precision bookkeeping is deferred, then done by up to 32 lanes at once
-// (16 where a single 12-warp CTA already needs nearly all of the shared memory)
-template <int N> __host__ __device__ constexpr int lik_pending() { return N > 224 ? 16 : 32; }
 // sentinels of the running minimum of firstele (real values are many orders of magnitude smaller):
 // outputs that are no window displacement carry FE_INVALID, a thread that has seen nothing FE_NONE
 constexpr float FE_INVALID = 1e36f, FE_NONE = 1e35f;
