@@ -1125,56 +1125,71 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
             bfft::Dft<R2, 1>::run(y);
             const int wa = 2 * (p0 + cc);
             const bool vb = wa + 1 < nw;
+            // firstele of the item's NK x 2 displacements (.x = row wa, .y = row wa + 1), all at once
+            float2 fe[NK];
             bfft::static_for<0, NK>([&](auto j_) {
               constexpr int j = decltype(j_)::value;
-              // .x = row wa, .y = row wa + 1
               const float2 v = bfft::cscale(y[k2_of(j)], p.invNN);
-              float2 fe = __fmul2_rn(v, v);
-              fe = __fadd2_rn(make_float2(f_a, f_a), make_float2(-fe.x, -fe.y));
-              fe = __fmul2_rn(make_float2(Nt, Nt), fe);
-              fe = __fadd2_rn(fe, __fmul2_rn(make_float2(f_b, f_b), v));
-              fe = __fadd2_rn(fe, make_float2(-f_c, -f_c));
-              fe = __fadd2_rn(fe, make_float2(-f_d, -f_d));
+              float2 f = __fmul2_rn(v, v);
+              f = __fadd2_rn(make_float2(f_a, f_a), make_float2(-f.x, -f.y));
+              f = __fmul2_rn(make_float2(Nt, Nt), f);
+              f = __fadd2_rn(f, __fmul2_rn(make_float2(f_b, f_b), v));
+              f = __fadd2_rn(f, make_float2(-f_c, -f_c));
+              f = __fadd2_rn(f, make_float2(-f_d, -f_d));
               const bool val = (vmask >> (t * NK + j)) & 1u;
-              fe.x = val ? fe.x : FE_INVALID;
-              fe.y = (val && vb) ? fe.y : FE_INVALID;
-              if (fminf(fe.x, fe.y) <= bfe)
-              {
-                // rare: a new minimum of this thread (ties resolved by the enumeration index);
-                // what has been summed so far is re-based onto it
+              fe[j].x = val ? f.x : FE_INVALID;
+              fe[j].y = (val && vb) ? f.y : FE_INVALID;
+            });
+            float mn = fminf(fe[0].x, fe[0].y);
+#pragma unroll
+            for (int j = 1; j < NK; j++)
+              mn = fminf(mn, fminf(fe[j].x, fe[j].y));
+            if (mn <= bfe)
+            {
+              // rare: a new minimum of this thread (ties resolved by the enumeration index);
+              // what has been summed so far is re-based onto it
+              const float old = bfe;
+              bfft::static_for<0, NK>([&](auto j_) {
+                constexpr int j = decltype(j_)::value;
                 const int wy = WT[k1 + R1 * k2_of(j)];
                 const int la = wa * nw + wy, lb = la + nw;
-                const float old = bfe;
-                if (fe.x < bfe || (fe.x == bfe && la < blin))
+                if (fe[j].x < bfe || (fe[j].x == bfe && la < blin))
                 {
-                  bfe = fe.x;
+                  bfe = fe[j].x;
                   blin = la;
-                  bv = v.x;
+                  bv = y[k2_of(j)].x * p.invNN;
                 }
-                if (fe.y < bfe || (fe.y == bfe && lb < blin))
+                if (fe[j].y < bfe || (fe[j].y == bfe && lb < blin))
                 {
-                  bfe = fe.y;
+                  bfe = fe[j].y;
                   blin = lb;
-                  bv = v.y;
+                  bv = y[k2_of(j)].y * p.invNN;
                 }
-                binv = __fdiv_rn(1.f, bfe);
-                const float sc = expa1p((old - bfe) * binv);
-                S2 = __fmul2_rn(S2, make_float2(sc, sc));
-              }
-              float2 tt = __fmul2_rn(__fadd2_rn(fe, make_float2(-bfe, -bfe)), make_float2(binv, binv));
+              });
+              binv = __fdiv_rn(1.f, bfe);
+              const float sc = expa1p((old - bfe) * binv);
+              S2 = __fmul2_rn(S2, make_float2(sc, sc));
+            }
+            bfft::static_for<0, NK>([&](auto j_) {
+              constexpr int j = decltype(j_)::value;
+              const float2 tt = __fmul2_rn(__fadd2_rn(fe[j], make_float2(-bfe, -bfe)), make_float2(binv, binv));
               float2 ll = __ffma2_rn(tt, make_float2(c3, c3), make_float2(c2, c2));
               ll = __ffma2_rn(tt, ll, make_float2(c1, c1));
               ll = __fmul2_rn(tt, ll);
               S2 = __fadd2_rn(S2, make_float2(ex2_ftz(ll.x), ex2_ftz(ll.y)));
-              if (p.dbg_values && ((vmask >> (t * NK + j)) & 1u))
-              {
-                const int wy = WT[k1 + R1 * k2_of(j)];
-                float *dv = p.dbg_values + ((size_t) oc * p.M + m) * nw * nw;
-                dv[wa * nw + wy] = v.x;
-                if (vb)
-                  dv[(wa + 1) * nw + wy] = v.y;
-              }
             });
+            if (p.dbg_values)
+              bfft::static_for<0, NK>([&](auto j_) {
+                constexpr int j = decltype(j_)::value;
+                if ((vmask >> (t * NK + j)) & 1u)
+                {
+                  const int wy = WT[k1 + R1 * k2_of(j)];
+                  float *dv = p.dbg_values + ((size_t) oc * p.M + m) * nw * nw;
+                  dv[wa * nw + wy] = y[k2_of(j)].x * p.invNN;
+                  if (vb)
+                    dv[(wa + 1) * nw + wy] = y[k2_of(j)].y * p.invNN;
+                }
+              });
           }
         }
         __syncwarp();
