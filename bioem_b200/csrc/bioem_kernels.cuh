@@ -663,18 +663,6 @@ template <int N> __host__ __device__ constexpr int lik_warps()
   return 8;
 #endif
 }
-// float4 operand pairs of the next column chunk that are loaded one chunk ahead (the rest is
-// loaded when the chunk starts).  Bounded by the 128-register budget of two CTAs per SM: measured
-// at N = 224, 2 pairs ahead 54.9 ns (no gain), 4 pairs 61.5 ns (spills), so the default is none.
-template <int N> __host__ __device__ constexpr int lik_prefetch()
-{
-#ifdef BIOEM_PF
-  return BIOEM_PF < Lay<N>::R1 / 2 ? BIOEM_PF : Lay<N>::R1 / 2;
-#else
-  return 0;
-#endif
-}
-
 template <int N> struct LikSmem
 {
   using L = Lay<N>;
@@ -965,22 +953,73 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
     __syncwarp();
   };
 
-  // Operands of the column chunk in flight: the loads of a warp's NEXT chunk are issued before the
-  // second radix pass of the current one (and those of the next likelihood's first chunk before
-  // the closing barrier), so that the L2 latency is covered by a whole chunk of work.
-  constexpr int PF = lik_prefetch<N>();
-  float4 Rq[PF > 0 ? PF : 1], Vq[PF > 0 ? PF : 1];
-  auto fetch = [&](int chn, const float4 *cv) {
-    const int base = chn * (R1 / 2) * KC * R2 + lane; // == main_idx(chn, 0, a_n2, a_c)
-#pragma unroll
-    for (int n1p = 0; n1p < PF; n1p++)
+  // The two radix passes of one column chunk (KC columns) of the current warp.
+  //   col1: loads, conv * conj(particle), radix-R1, twiddle -> the warp's exchange tile
+  //   col2: radix-R2 (pruned) from the tile -> row slots of Y
+  auto col1 = [&](int ch, const float4 *conv) {
+    if (a_act)
     {
-      Rq[n1p] = ldg4(ref + base + n1p * KC * R2);
-      Vq[n1p] = ldg4(cv + base + n1p * KC * R2);
+      float2 x[R1];
+      const int base = ch * (R1 / 2) * KC * R2 + lane; // == main_idx(ch, 0, a_n2, a_c)
+#pragma unroll
+      for (int n1p = 0; n1p < R1 / 2; n1p++)
+      {
+        const float4 r = ldg4(ref + base + n1p * KC * R2);
+        const float4 v = ldg4(conv + base + n1p * KC * R2);
+        x[2 * n1p] = bfft::cmulc(make_float2(v.x, v.y), make_float2(r.x, r.y));
+        x[2 * n1p + 1] = bfft::cmulc(make_float2(v.z, v.w), make_float2(r.z, r.w));
+      }
+      if (ch == 0 && a_c == 0)
+      {
+        // pack the Nyquist column into the (Hermitian) DC column: Z = X0 + i*X_{N/2}
+#pragma unroll
+        for (int n1p = 0; n1p < R1 / 2; n1p++)
+        {
+          const float4 r = ldg4(ref + L::MAIN4 + n1p * R2 + a_n2);
+          const float4 v = ldg4(conv + L::MAIN4 + n1p * R2 + a_n2);
+          x[2 * n1p] = bfft::cadd_i(x[2 * n1p], bfft::cmulc(make_float2(v.x, v.y), make_float2(r.x, r.y)));
+          x[2 * n1p + 1] = bfft::cadd_i(x[2 * n1p + 1], bfft::cmulc(make_float2(v.z, v.w), make_float2(r.z, r.w)));
+        }
+      }
+      bfft::Dft<R1, 1>::run(x);
+#pragma unroll
+      for (int k1 = 1; k1 < R1; k1++)
+        x[k1] = bfft::cmul(x[k1], tw[k1]);
+#pragma unroll
+      for (int k1 = 0; k1 < R1; k1++)
+        E[k1 * ES + a_c * CS + a_n2] = x[k1];
     }
+    __syncwarp();
   };
-  if (PF > 0 && a_act && warp < NCH && o_lo < o_hi)
-    fetch(warp, p.convs + (size_t) o_lo * p.C * L::MAP4);
+  auto col2 = [&](int ch) {
+#pragma unroll
+    for (int t = 0; t < P2; t++)
+    {
+      const int item = lane + 32 * t;
+      if (item < KC * R1)
+      {
+        const int k1 = item / KC, cc = item % KC;
+        float2 y[R2];
+#pragma unroll
+        for (int n2 = 0; n2 < R2; n2++)
+          y[n2] = E[k1 * ES + cc * CS + n2];
+        bfft::Dft<R2, 1>::run(y);
+        float2 *Ycol = Y + k1 * YS + ch * KC + cc;
+        bfft::static_for<0, NK>([&](auto j_) {
+          constexpr int j = decltype(j_)::value;
+          Ycol[j * R1 * YS] = y[k2_of(j)];
+        });
+      }
+    }
+    __syncwarp();
+  };
+  // Row tasks (KC row pairs each) are dealt round robin, so the last round is not full: the warps
+  // without a task in it run the first radix pass of their first column chunk of the NEXT
+  // likelihood before the closing barrier instead of idling (its operands do not depend on Y).
+  const int npairs_all = nwp / 2;
+  const int row_rounds = (npairs_all + NWARP * KC - 1) / (NWARP * KC);
+  const bool short_rows = warp * KC + (row_rounds - 1) * NWARP * KC >= npairs_all; // no task in the last round
+  bool pre_done = false;
 
   for (int ol = o_lo; ol < o_hi; ol++)
   {
@@ -1005,63 +1044,11 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
       // ------------------------------------------------ column pass (along kx), per warp
       for (int ch = warp; ch < NCH; ch += NWARP)
       {
-        if (a_act)
-        {
-          float2 x[R1];
-#pragma unroll
-          const int base = ch * (R1 / 2) * KC * R2 + lane; // == main_idx(ch, 0, a_n2, a_c)
-#pragma unroll
-          for (int n1p = 0; n1p < R1 / 2; n1p++)
-          {
-            const float4 r = n1p < PF ? Rq[n1p] : ldg4(ref + base + n1p * KC * R2);
-            const float4 v = n1p < PF ? Vq[n1p] : ldg4(conv + base + n1p * KC * R2);
-            x[2 * n1p] = bfft::cmulc(make_float2(v.x, v.y), make_float2(r.x, r.y));
-            x[2 * n1p + 1] = bfft::cmulc(make_float2(v.z, v.w), make_float2(r.z, r.w));
-          }
-          if (ch == 0 && a_c == 0)
-          {
-            // pack the Nyquist column into the (Hermitian) DC column: Z = X0 + i*X_{N/2}
-#pragma unroll
-            for (int n1p = 0; n1p < R1 / 2; n1p++)
-            {
-              const float4 r = ldg4(ref + L::MAIN4 + n1p * R2 + a_n2);
-              const float4 v = ldg4(conv + L::MAIN4 + n1p * R2 + a_n2);
-              x[2 * n1p] = bfft::cadd_i(x[2 * n1p], bfft::cmulc(make_float2(v.x, v.y), make_float2(r.x, r.y)));
-              x[2 * n1p + 1] = bfft::cadd_i(x[2 * n1p + 1], bfft::cmulc(make_float2(v.z, v.w), make_float2(r.z, r.w)));
-            }
-          }
-          bfft::Dft<R1, 1>::run(x);
-#pragma unroll
-          for (int k1 = 1; k1 < R1; k1++)
-            x[k1] = bfft::cmul(x[k1], tw[k1]);
-#pragma unroll
-          for (int k1 = 0; k1 < R1; k1++)
-            E[k1 * ES + a_c * CS + a_n2] = x[k1];
-        }
-        __syncwarp();
-        if (PF > 0 && a_act && ch + NWARP < NCH)
-          fetch(ch + NWARP, conv);
-#pragma unroll
-        for (int t = 0; t < P2; t++)
-        {
-          const int item = lane + 32 * t;
-          if (item < KC * R1)
-          {
-            const int k1 = item / KC, cc = item % KC;
-            float2 y[R2];
-#pragma unroll
-            for (int n2 = 0; n2 < R2; n2++)
-              y[n2] = E[k1 * ES + cc * CS + n2];
-            bfft::Dft<R2, 1>::run(y);
-            float2 *Ycol = Y + k1 * YS + ch * KC + cc;
-            bfft::static_for<0, NK>([&](auto j_) {
-              constexpr int j = decltype(j_)::value;
-              Ycol[j * R1 * YS] = y[k2_of(j)];
-            });
-          }
-        }
-        __syncwarp();
+        if (!(pre_done && ch == warp))
+          col1(ch, conv);
+        col2(ch);
       }
+      pre_done = false;
       __syncthreads(); // all candidate rows of all columns are in Y
 
       // ------------------------------------------------ row pass (along ky), 2 rows per transform
@@ -1225,8 +1212,11 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
         s_wc[slot][warp] = cand;
         s_ws[slot][warp] = S;
       }
-      if (PF > 0 && a_act && warp < NCH && oc + 1 < o_hi * p.C)
-        fetch(warp, conv + L::MAP4); // first chunk of the next likelihood (next conv spectrum of the batch)
+      if (short_rows && warp < NCH && oc + 1 < o_hi * p.C)
+      {
+        col1(warp, conv + L::MAP4); // the next conv spectrum of the batch follows this one
+        pre_done = true;
+      }
       __syncthreads(); // Y consumed (the next column pass may overwrite it), ring entry complete
       slot++;
       if (slot == NPEND || (p.angles && c == p.C - 1))
