@@ -681,50 +681,6 @@ template <int N> __host__ __device__ constexpr size_t lik_smem_bytes(int maxD)
   return LikSmem<N>::bytes(lik_window_groups<N>(maxD));
 }
 
-// ---------------------------------------------------------------------------
-// Tensor memory (TMEM, 256 KB per SM, otherwise unused by this tensor-core-free kernel) as a
-// per-lane extension of the register file: every warp parks its lane-constant inter-stage twiddles
-// there (tcgen05.st, 32 lanes x 32 columns of 32 bits) and fetches them (tcgen05.ld) only for the
-// few instructions that multiply by them, which frees 2*(R1-1) registers per thread for the rest
-// of the two radix passes.
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ void tmem_alloc(unsigned *smem_slot, unsigned ncols) // one whole warp
-{
-  const unsigned a = (unsigned) __cvta_generic_to_shared(smem_slot);
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(a), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(unsigned taddr, unsigned ncols) // one whole warp
-{
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tmem_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tmem_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-// 32 consecutive columns of this thread's TMEM lane <-> 32 registers
-__device__ __forceinline__ void tmem_st32(unsigned taddr, const unsigned (&r)[32])
-{
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
-               "%15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
-               "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
-               "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
-               "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
-               "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-               : "memory");
-  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_ld32(unsigned taddr, unsigned (&r)[32])
-{
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-               "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                 "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-                 "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-                 "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-               : "r"(taddr)
-               : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
 // 2^x, one MUFU.EX2 (results below the normal range flush to zero)
 __device__ __forceinline__ float ex2_ftz(float x)
 {
@@ -845,49 +801,10 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
   // (c = column / row pair within the warp's task, n2 = sub-sequence).  Pass 2: item = k1*KC + c.
   const int a_c = lane / R2, a_n2 = lane % R2;
   const bool a_act = lane < KC * R2;
-  // inter-stage twiddles exp(+2 pi i n2*k1/N), k1 = 0..R1-1, of this lane's sub-sequence: parked in
-  // tensor memory, columns [32*i, 32*i+32) of the warp's TMEM lanes hold twiddles 16*i .. 16*i+15
-  constexpr int NTW = (2 * R1 + 31) / 32;                                 // 32-column pieces per warp
-  constexpr unsigned TCOLS_NEED = ((NWARP + 3) / 4) * NTW * 32;           // warps w and w+4 share TMEM lanes
-  constexpr unsigned TCOLS = TCOLS_NEED <= 32 ? 32 : TCOLS_NEED <= 64 ? 64 : TCOLS_NEED <= 128 ? 128 : TCOLS_NEED <= 256 ? 256 : 512;
-  __shared__ unsigned s_tmem;
-  if (warp == 0)
-    tmem_alloc(&s_tmem, TCOLS);
-  tmem_fence_before();
-  __syncthreads();
-  tmem_fence_after();
-  const unsigned tmem_base = s_tmem;
-  const unsigned tw_addr = tmem_base + ((unsigned) (32 * (warp & 3)) << 16) + (unsigned) ((warp >> 2) * NTW * 32);
+  float2 tw[R1]; // exp(+2 pi i n2*k1/N), k1 >= 1
 #pragma unroll
-  for (int i = 0; i < NTW; i++)
-  {
-    unsigned r[32];
-#pragma unroll
-    for (int e = 0; e < 16; e++)
-    {
-      const int k1 = 16 * i + e;
-      const float2 w = k1 < R1 ? p.tw_inv[a_n2 * R1 + k1] : make_float2(0.f, 0.f);
-      r[2 * e] = __float_as_uint(w.x);
-      r[2 * e + 1] = __float_as_uint(w.y);
-    }
-    tmem_st32(tw_addr + 32 * i, r);
-  }
-  // x[k1] *= twiddle(k1) for all k1, twiddles fetched from tensor memory (all 32 lanes take part)
-  auto twiddle = [&](float2 *x) {
-#pragma unroll
-    for (int i = 0; i < NTW; i++)
-    {
-      unsigned r[32];
-      tmem_ld32(tw_addr + 32 * i, r);
-#pragma unroll
-      for (int e = 0; e < 16; e++)
-      {
-        const int k1 = 16 * i + e;
-        if (k1 >= 1 && k1 < R1)
-          x[k1] = bfft::cmul(x[k1], make_float2(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1])));
-      }
-    }
-  };
+  for (int k1 = 1; k1 < R1; k1++)
+    tw[k1] = p.tw_inv[a_n2 * R1 + k1];
   // bit t*NK + j: output j of this lane's pass-2 item t is a window displacement (the others are
   // computed too, but enter the minimum / sum as FE_INVALID)
   unsigned vmask = 0;
@@ -1040,9 +957,9 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
   //   col1: loads, conv * conj(particle), radix-R1, twiddle -> the warp's exchange tile
   //   col2: radix-R2 (pruned) from the tile -> row slots of Y
   auto col1 = [&](int ch, const float4 *conv) {
-    float2 x[R1];
     if (a_act)
     {
+      float2 x[R1];
       const int base = ch * (R1 / 2) * KC * R2 + lane; // == main_idx(ch, 0, a_n2, a_c)
 #pragma unroll
       for (int n1p = 0; n1p < R1 / 2; n1p++)
@@ -1065,17 +982,9 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
         }
       }
       bfft::Dft<R1, 1>::run(x);
-    }
-    else
-    {
 #pragma unroll
-      for (int k1 = 0; k1 < R1; k1++)
-        x[k1] = make_float2(0.f, 0.f);
-    }
-    __syncwarp();
-    twiddle(x);
-    if (a_act)
-    {
+      for (int k1 = 1; k1 < R1; k1++)
+        x[k1] = bfft::cmul(x[k1], tw[k1]);
 #pragma unroll
       for (int k1 = 0; k1 < R1; k1++)
         E[k1 * ES + a_c * CS + a_n2] = x[k1];
@@ -1152,52 +1061,41 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
       for (int p0 = warp * KC; p0 < npairs; p0 += NWARP * KC)
       {
         const int npl = min(KC, npairs - p0);
+        if (a_act && a_c < npl)
         {
-          const bool act1 = a_act && a_c < npl;
+          const float2 *Ya = Y + (size_t) RS[2 * (p0 + a_c)] * YS;
+          const float2 *Yb = Y + (size_t) RS[2 * (p0 + a_c) + 1] * YS;
           float2 x[R1];
-          if (act1)
-          {
-            const float2 *Ya = Y + (size_t) RS[2 * (p0 + a_c)] * YS;
-            const float2 *Yb = Y + (size_t) RS[2 * (p0 + a_c) + 1] * YS;
 #pragma unroll
-            for (int n1 = 0; n1 < R1; n1++)
+          for (int n1 = 0; n1 < R1; n1++)
+          {
+            if (n1 < R1 / 2)
             {
-              if (n1 < R1 / 2)
-              {
-                const float2 a = Ya[n1 * R2 + a_n2], b = Yb[n1 * R2 + a_n2];
-                x[n1] = bfft::cadd_i(a, b); // A[n] + i*B[n]
-              }
-              else
-              {
-                // n = n1*R2 + n2 >= N/2: A[n] = conj(A[N-n])
-                const int nm = (R1 - n1) * R2 - a_n2;
-                const float2 a = Ya[nm], b = Yb[nm];
-                x[n1] = __fadd2_rn(make_float2(a.x, -a.y), make_float2(b.y, b.x));
-              }
+              const float2 a = Ya[n1 * R2 + a_n2], b = Yb[n1 * R2 + a_n2];
+              x[n1] = bfft::cadd_i(a, b); // A[n] + i*B[n]
             }
-            if (a_n2 == 0)
+            else
             {
-              // DC and Nyquist of the two (real) columns ky = 0 and ky = N/2 share slot 0
-              const float2 a = Ya[0], b = Yb[0];
-              x[0] = make_float2(a.x, b.x);
-              x[R1 / 2] = make_float2(a.y, b.y);
+              // n = n1*R2 + n2 >= N/2: A[n] = conj(A[N-n])
+              const int nm = (R1 - n1) * R2 - a_n2;
+              const float2 a = Ya[nm], b = Yb[nm];
+              x[n1] = __fadd2_rn(make_float2(a.x, -a.y), make_float2(b.y, b.x));
             }
-            bfft::Dft<R1, 1>::run(x);
           }
-          else
+          if (a_n2 == 0)
           {
-#pragma unroll
-            for (int k1 = 0; k1 < R1; k1++)
-              x[k1] = make_float2(0.f, 0.f);
+            // DC and Nyquist of the two (real) columns ky = 0 and ky = N/2 share slot 0
+            const float2 a = Ya[0], b = Yb[0];
+            x[0] = make_float2(a.x, b.x);
+            x[R1 / 2] = make_float2(a.y, b.y);
           }
-          __syncwarp();
-          twiddle(x);
-          if (act1)
-          {
+          bfft::Dft<R1, 1>::run(x);
 #pragma unroll
-            for (int k1 = 0; k1 < R1; k1++)
-              E[k1 * ES + a_c * CS + a_n2] = x[k1];
-          }
+          for (int k1 = 1; k1 < R1; k1++)
+            x[k1] = bfft::cmul(x[k1], tw[k1]);
+#pragma unroll
+          for (int k1 = 0; k1 < R1; k1++)
+            E[k1 * ES + a_c * CS + a_n2] = x[k1];
         }
         __syncwarp(); // also: every read of this task's Y rows is done, their slots may take FE
 #pragma unroll
@@ -1338,10 +1236,6 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
   }
   if (warp == 0 && slot > 0)
     flush(slot);
-  tmem_fence_before();
-  __syncthreads();
-  if (warp == 0)
-    tmem_dealloc(tmem_base, TCOLS);
   if (tid == 0)
   {
     Running r;
