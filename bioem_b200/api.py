@@ -46,13 +46,15 @@ EXPORTS = [
     "bioem_b200_last_error", "bioem_b200_version", "bioem_b200_device_count",
     "bioem_b200_supported_size", "bioem_b200_create", "bioem_b200_destroy",
     "bioem_b200_upload_model", "bioem_b200_upload_orientations", "bioem_b200_upload_ctf",
-    "bioem_b200_upload_particles", "bioem_b200_upload_particles_fft", "bioem_b200_reset",
+    "bioem_b200_upload_ctf_real", "bioem_b200_upload_particles", "bioem_b200_upload_particles_fft",
+    "bioem_b200_reset",
     "bioem_b200_run", "bioem_b200_synchronize", "bioem_b200_download",
     "bioem_b200_partial_bytes", "bioem_b200_export_partial", "bioem_b200_import_partials",
     "bioem_b200_merge_host", "bioem_b200_stream", "bioem_b200_device_angles", "bioem_b200_stats",
     "bioem_b200_kernel_time", "bioem_b200_debug_projection", "bioem_b200_debug_convolved",
     "bioem_b200_debug_correlation", "bioem_b200_debug_particle",
-    "bioem_b200_host_defocus_to_phase", "bioem_b200_host_ctf_table", "bioem_b200_host_volu",
+    "bioem_b200_host_defocus_to_phase", "bioem_b200_host_ctf_table", "bioem_b200_host_psf_kernels",
+    "bioem_b200_host_volu",
     "bioem_b200_host_model_prepare", "bioem_b200_host_normalise_map",
     "bioem_b200_host_final_logprob",
 ]
@@ -84,6 +86,7 @@ def lib():
     L.bioem_b200_upload_model.argtypes = [vp, vp, C.c_int, C.c_float]
     L.bioem_b200_upload_orientations.argtypes = [vp, fp, C.c_int]
     L.bioem_b200_upload_ctf.argtypes = [vp, fp, fp, C.c_int]
+    L.bioem_b200_upload_ctf_real.argtypes = [vp, fp, fp, C.c_int]
     L.bioem_b200_upload_particles.argtypes = [vp, fp, C.c_int]
     L.bioem_b200_upload_particles_fft.argtypes = [vp, fp, fp, fp, C.c_int]
     L.bioem_b200_reset.argtypes = [vp]
@@ -110,6 +113,9 @@ def lib():
     L.bioem_b200_host_ctf_table.argtypes = [C.c_int, C.c_float, C.c_int, C.c_float, C.c_float,
                                             C.c_int, C.c_float, C.c_float, C.c_int, C.c_float,
                                             C.c_float, C.c_int, fp, fp, fp]
+    L.bioem_b200_host_psf_kernels.argtypes = [C.c_int, C.c_float, C.c_float, C.c_float, C.c_int,
+                                              C.c_float, C.c_float, C.c_int, C.c_float, C.c_float,
+                                              C.c_int, fp, fp, fp]
     L.bioem_b200_host_volu.argtypes = [C.c_float, C.c_int, C.c_float, C.c_int, C.c_int, C.c_float,
                                        C.c_float, C.c_float, C.c_float, C.c_float]
     L.bioem_b200_host_volu.restype = C.c_float
@@ -150,21 +156,36 @@ class HostInputs:
         cen_d = C.c_float(ctf.get("PRIOR_DEFOCUS_CENTER", 3.0))
         sig_a = f32(ctf.get("SIGMA_PRIOR_AMP_CTF", 0.5))
         cen_a = f32(ctf.get("PRIOR_AMP_CTF_CENTER", 0.0))
-        d0, d1, nd = ctf["CTF_DEFOCUS"]
-        b0, b1, nb = ctf["CTF_B_ENV"]
-        a0, a1, na = ctf["CTF_AMPLITUDE"]
-        p0, p1 = C.c_float(), C.c_float()
-        L.bioem_b200_host_defocus_to_phase(f32(d0), f32(d1), f32(elecwavel), C.byref(p0), C.byref(p1),
-                                           C.byref(cen_d), C.byref(sig_d))
-        self.C = int(na) * int(nd) * int(nb)
-        self.refCTF = np.zeros((self.C, self.F, 2), dtype=np.float32)
-        self.CtfParam = np.zeros((self.C, 4), dtype=np.float32)
+        self.use_psf = "PSF_PHASE" in ctf
         grids = np.zeros(3, dtype=np.float32)
-        c = L.bioem_b200_host_ctf_table(n, f32(pixel_size), 0, f32(a0), f32(a1), int(na), p0, p1, int(nd),
-                                        f32(b0), f32(b1), int(nb), _fp(self.refCTF), _fp(self.CtfParam),
-                                        _fp(grids))
+        if not self.use_psf:
+            d0, d1, nd = ctf["CTF_DEFOCUS"]
+            b0, b1, nb = ctf["CTF_B_ENV"]
+            a0, a1, na = ctf["CTF_AMPLITUDE"]
+            p0, p1 = C.c_float(), C.c_float()
+            L.bioem_b200_host_defocus_to_phase(f32(d0), f32(d1), f32(elecwavel), C.byref(p0), C.byref(p1),
+                                               C.byref(cen_d), C.byref(sig_d))
+            self.C = int(na) * int(nd) * int(nb)
+            self.refCTF = np.zeros((self.C, self.F, 2), dtype=np.float32)
+            self.CtfParam = np.zeros((self.C, 4), dtype=np.float32)
+            c = L.bioem_b200_host_ctf_table(n, f32(pixel_size), 0, f32(a0), f32(a1), int(na), p0, p1, int(nd),
+                                            f32(b0), f32(b1), int(nb), _fp(self.refCTF), _fp(self.CtfParam),
+                                            _fp(grids))
+            self.psf_kernels = None
+        else:
+            # USE_PSF (reference param.cpp:1466-1535): kernels in real space, transformed on the device
+            p0, p1, nd = ctf["PSF_PHASE"]
+            b0, b1, nb = ctf["PSF_ENVELOPE"]
+            a0, a1, na = ctf["PSF_AMPLITUDE"]
+            self.C = int(na) * int(nd) * int(nb)
+            self.refCTF = None
+            self.psf_kernels = np.zeros((self.C, n, n), dtype=np.float32)
+            self.CtfParam = np.zeros((self.C, 4), dtype=np.float32)
+            c = L.bioem_b200_host_psf_kernels(n, f32(pixel_size), f32(a0), f32(a1), int(na), f32(p0), f32(p1),
+                                              int(nd), f32(b0), f32(b1), int(nb), _fp(self.psf_kernels),
+                                              _fp(self.CtfParam), _fp(grids))
         if c != self.C:
-            raise BioemError(f"host_ctf_table returned {c}, expected {self.C}")
+            raise BioemError(f"CTF / PSF table: {c} kernels, expected {self.C}")
         self.angles = np.ascontiguousarray(orientations, dtype=np.float32)
         if self.angles.shape[1] == 3:
             self.angles = np.concatenate([self.angles, np.zeros((len(self.angles), 1), np.float32)], 1)
@@ -172,7 +193,8 @@ class HostInputs:
         voluang = f32(1.0 / float(f32(self.O)) * float(f32(prior_mod)))  # list: reference param.cpp:1131,1324
         volu = L.bioem_b200_host_volu(voluang, int(grid_space), f32(pixel_size), int(max_disp), int(na),
                                       grids[2], grids[1], sig_b, sig_d, sig_a)
-        self.cfg = Config(n, int(max_disp), int(grid_space), int(write_angles), 0, int(quaternions), 0, 0,
+        self.cfg = Config(n, int(max_disp), int(grid_space), int(write_angles), int(self.use_psf),
+                          int(quaternions), 0, 0,
                           f32(pixel_size), f32(n * n), volu, sig_b, sig_d, cen_d, sig_a, cen_a)
         m = np.asarray(model, dtype=np.float32)
         self.points = np.zeros(m.shape[0], dtype=MODEL_POINT_DTYPE)
@@ -235,6 +257,13 @@ class Engine:
         assert p.shape == (self.C, 4)
         _chk(lib().bioem_b200_upload_ctf(self._h, _fp(r), _fp(p), self.C), "upload_ctf")
 
+    def upload_ctf_real(self, kernels: np.ndarray, ctf_param4: np.ndarray):
+        self.C = kernels.shape[0]
+        k = np.ascontiguousarray(kernels, dtype=np.float32)
+        p = np.ascontiguousarray(ctf_param4, dtype=np.float32)
+        assert p.shape == (self.C, 4)
+        _chk(lib().bioem_b200_upload_ctf_real(self._h, _fp(k), _fp(p), self.C), "upload_ctf_real")
+
     def upload_particles(self, maps: np.ndarray):
         m = np.ascontiguousarray(maps, dtype=np.float32)
         self.M = m.shape[0]
@@ -250,7 +279,10 @@ class Engine:
     def upload_all(self, hi: HostInputs, particles: np.ndarray):
         self.upload_model(hi.points, hi.NormDen)
         self.upload_orientations(hi.angles)
-        self.upload_ctf(hi.refCTF, hi.CtfParam)
+        if hi.use_psf:
+            self.upload_ctf_real(hi.psf_kernels, hi.CtfParam)
+        else:
+            self.upload_ctf(hi.refCTF, hi.CtfParam)
         self.upload_particles(particles)
 
     # ---- run

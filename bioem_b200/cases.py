@@ -10,6 +10,9 @@ import numpy as np
 from . import synth
 
 CFG1_CTF = dict(CTF_DEFOCUS=(1.0, 4.0, 3), CTF_B_ENV=(2.0, 300.0, 1), CTF_AMPLITUDE=(0.1, 0.1, 1))
+# USE_PSF (real-space point-spread functions): phase / envelope in 1/A^2 (reference doc, PSF keywords)
+PSF_GRID = dict(PSF_PHASE=(0.004, 0.016, 3), PSF_ENVELOPE=(0.006, 0.018, 2), PSF_AMPLITUDE=(0.1, 0.1, 1),
+                SIGMA_PRIOR_B_CTF=200.0, SIGMA_PRIOR_DEFOCUS=8000.0, PRIOR_DEFOCUS_CENTER=3000.0)
 DENSE_CTF = dict(CTF_DEFOCUS=(0.5, 4.5, 16), CTF_B_ENV=(2.0, 300.0, 8),
                  CTF_AMPLITUDE=(0.05, 0.25, 2), SIGMA_PRIOR_B_CTF=50.0,
                  SIGMA_PRIOR_DEFOCUS=0.4, PRIOR_DEFOCUS_CENTER=2.8)
@@ -33,7 +36,13 @@ class Case:
     particle_format: str = "text"   # "text" | "mrc"
 
     @property
+    def use_psf(self) -> bool:
+        return "PSF_PHASE" in self.ctf
+
+    @property
     def n_ctf(self) -> int:
+        if self.use_psf:
+            return int(self.ctf["PSF_AMPLITUDE"][2] * self.ctf["PSF_PHASE"][2] * self.ctf["PSF_ENVELOPE"][2])
         return int(self.ctf["CTF_AMPLITUDE"][2] * self.ctf["CTF_DEFOCUS"][2] * self.ctf["CTF_B_ENV"][2])
 
     @property
@@ -45,6 +54,7 @@ CASES = {
     # tiny known-answer cases (oracle / reference finish in well under a second)
     "toy32": Case("toy32", 32, 1.5, 60, 3, 576, 24, CFG1_CTF, 4, 1, write_angles=3,
                   model_sigma=5.0, model_rmax=12.0),
+    "toy32psf": Case("toy32psf", 32, 1.5, 60, 3, 576, 16, PSF_GRID, 4, 1, model_sigma=5.0, model_rmax=12.0),
     "toy36g2": Case("toy36g2", 36, 1.5, 60, 4, 576, 16, CFG1_CTF, 6, 2, model_sigma=6.0,
                     model_rmax=14.0, particle_format="mrc"),
     "toy64": Case("toy64", 64, 1.5, 200, 5, 576, 32, synth.PRODUCTION_GRID, 10, 1,
@@ -84,7 +94,7 @@ def build_case(name_or_case, outdir: str | None = None, n_particles: int | None 
                     "n_orient": n_orient or c.n_orient})
     model = synth.make_model(c.n_atoms, seed=1, sigma=c.model_sigma, rmax=c.model_rmax)
     quats = synth.load_quaternions(c.quat_list)[:c.n_orient].copy()
-    ctfp = synth.ctf_grid_params(c.ctf)
+    ctfp = synth.ctf_grid_params(CFG1_CTF if c.use_psf else c.ctf)
     imgs, truth = synth.make_particles(model, quats, c.n_pixels, c.pixel_size, c.n_particles,
                                        c.max_disp, ctfp, snr=0.1, seed=100,
                                        normalise=(c.particle_format == "mrc"))
@@ -100,7 +110,7 @@ def build_case(name_or_case, outdir: str | None = None, n_particles: int | None 
                                             else "particles.txt"))
         synth.write_model_text(paths["model"], model)
         synth.write_param_file(paths["param"], c.n_pixels, c.pixel_size, c.max_disp, c.grid_space,
-                               c.ctf, True, c.write_angles)
+                               c.ctf, True, c.write_angles, extra=["USE_PSF"] if c.use_psf else None)
         synth.write_orientation_list(paths["orient"], quats)
         if c.particle_format == "mrc":
             synth.write_particles_mrc(paths["particles"], imgs)

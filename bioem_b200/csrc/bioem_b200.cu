@@ -243,6 +243,42 @@ static size_t smem_for(int N, int maxD)
   return 0;
 }
 
+// Gaussian priors on the CTF parameters (bioem_algorithm.h:49-67), per kernel, in double
+static int set_ctf_priors(bioem_b200_context *h, const float *CtfParam4, int C)
+{
+  std::vector<double> prior(C);
+  const bioem_b200_config &p = h->cfg;
+  for (int c = 0; c < C; c++)
+  {
+    const float amp = CtfParam4[4 * c], pha = CtfParam4[4 * c + 1], env = CtfParam4[4 * c + 2];
+    double pr;
+    if (!p.tousepsf)
+    {
+      pr = env * env / 2. / p.sigmaPriorbctf / p.sigmaPriorbctf -
+           (pha - p.Priordefcent) * (pha - p.Priordefcent) / 2. / p.sigmaPriordefo / p.sigmaPriordefo -
+           (amp - p.Priorampcent) * (amp - p.Priorampcent) / 2. / p.sigmaPrioramp / p.sigmaPrioramp;
+    }
+    else
+    {
+      // PSF parameters are mapped to their Fourier-space counterparts first (bioem_algorithm.h:59-66)
+      const double envF = 4. * M_PI * M_PI * env / (env * env + pha * pha);
+      const double phaF = 4. * M_PI * M_PI * pha / (env * env + pha * pha);
+      pr = envF * envF / 2. / p.sigmaPriorbctf / p.sigmaPriorbctf -
+           (phaF - p.Priordefcent) * (phaF - p.Priordefcent) / 2. / p.sigmaPriordefo / p.sigmaPriordefo -
+           (amp - p.Priorampcent) * (amp - p.Priorampcent) / 2. / p.sigmaPrioramp / p.sigmaPrioramp;
+    }
+    prior[c] = pr;
+  }
+  cudaFree(h->d_prior);
+  h->d_prior = nullptr;
+  CU(cudaMalloc(&h->d_prior, sizeof(double) * C));
+  CU(cudaMemcpy(h->d_prior, prior.data(), sizeof(double) * C, cudaMemcpyHostToDevice));
+  if (C != h->C)
+    free_batch(h);
+  h->C = C;
+  return BIOEM_B200_OK;
+}
+
 // ---------------------------------------------------------------------------------
 extern "C" {
 
@@ -405,41 +441,36 @@ int bioem_b200_upload_ctf(bioem_b200_handle h, const float *refCTF, const float 
   CU(cudaMalloc(&tmp, sizeof(float2) * stdsz * C));
   CU(cudaMemcpy(tmp, refCTF, sizeof(float2) * stdsz * C, cudaMemcpyHostToDevice));
   cudaFree(h->d_ctf);
-  cudaFree(h->d_prior);
+  h->d_ctf = nullptr;
   CU(cudaMalloc(&h->d_ctf, sizeof(float4) * h->map4 * C));
   CU(do_pack(N, tmp, h->d_ctf, C, h->stream));
   h->launches++;
-  // Gaussian priors on the CTF parameters (bioem_algorithm.h:49-67), per kernel, in double
-  std::vector<double> prior(C);
-  const bioem_b200_config &p = h->cfg;
-  for (int c = 0; c < C; c++)
-  {
-    const float amp = CtfParam4[4 * c], pha = CtfParam4[4 * c + 1], env = CtfParam4[4 * c + 2];
-    double pr;
-    if (!p.tousepsf)
-    {
-      pr = env * env / 2. / p.sigmaPriorbctf / p.sigmaPriorbctf -
-           (pha - p.Priordefcent) * (pha - p.Priordefcent) / 2. / p.sigmaPriordefo / p.sigmaPriordefo -
-           (amp - p.Priorampcent) * (amp - p.Priorampcent) / 2. / p.sigmaPrioramp / p.sigmaPrioramp;
-    }
-    else
-    {
-      const double envF = 4. * M_PI * M_PI * env / (env * env + pha * pha);
-      const double phaF = 4. * M_PI * M_PI * pha / (env * env + pha * pha);
-      pr = envF * envF / 2. / p.sigmaPriorbctf / p.sigmaPriorbctf -
-           (phaF - p.Priordefcent) * (phaF - p.Priordefcent) / 2. / p.sigmaPriordefo / p.sigmaPriordefo -
-           (amp - p.Priorampcent) * (amp - p.Priorampcent) / 2. / p.sigmaPrioramp / p.sigmaPrioramp;
-    }
-    prior[c] = pr;
-  }
-  CU(cudaMalloc(&h->d_prior, sizeof(double) * C));
-  CU(cudaMemcpyAsync(h->d_prior, prior.data(), sizeof(double) * C, cudaMemcpyHostToDevice, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   cudaFree(tmp);
-  if (C != h->C)
-    free_batch(h);
-  h->C = C;
-  return BIOEM_B200_OK;
+  return set_ctf_priors(h, CtfParam4, C);
+}
+
+int bioem_b200_upload_ctf_real(bioem_b200_handle h, const float *kernels, const float *CtfParam4, int C)
+{
+  if (!h || !kernels || !CtfParam4 || C <= 0)
+    return fail(BIOEM_B200_ERR_INVALID, "upload_ctf_real: bad argument");
+  CU(cudaSetDevice(h->device));
+  const int N = h->N;
+  const size_t n2 = (size_t) N * N;
+  float *d_img = nullptr;
+  float2 *d_scr = nullptr;
+  CU(cudaMalloc(&d_img, sizeof(float) * n2 * C));
+  CU(cudaMalloc(&d_scr, sizeof(float2) * (size_t) N * (N / 2 + 1) * C));
+  CU(cudaMemcpy(d_img, kernels, sizeof(float) * n2 * C, cudaMemcpyHostToDevice));
+  cudaFree(h->d_ctf);
+  h->d_ctf = nullptr;
+  CU(cudaMalloc(&h->d_ctf, sizeof(float4) * h->map4 * C));
+  CU(do_fft2d(N, d_img, nullptr, 0, 0.f, h->d_tw_fwd, d_scr, h->d_ctf, C, h->stream));
+  h->launches += 2;
+  CU(cudaStreamSynchronize(h->stream));
+  cudaFree(d_img);
+  cudaFree(d_scr);
+  return set_ctf_priors(h, CtfParam4, C);
 }
 
 static int set_particle_count(bioem_b200_context *h, int M)
@@ -553,7 +584,6 @@ static int ensure_batch(bioem_b200_context *h)
   h->nbands = (int) (((size_t) N * N * 4 + band_budget - 1) / band_budget);
   h->band_rows = (N + h->nbands - 1) / h->nbands;
   h->nbands = (N + h->band_rows - 1) / h->band_rows;
-  CU(cudaFuncSetAttribute(project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ((size_t) h->band_rows * N * 4)));
   CU(cudaMalloc(&h->d_proj, sizeof(float) * (size_t) N * N * h->OB));
   CU(cudaMalloc(&h->d_tempden, sizeof(double) * h->nbands * h->OB));
   CU(cudaMalloc(&h->d_scratch, sizeof(float2) * (size_t) N * (N / 2 + 1) * h->OB));
@@ -618,6 +648,9 @@ static int run_front(bioem_b200_context *h, int o0, int OBcur)
   pp.shiftY = h->cfg.shiftY;
   pp.pixelSize = h->cfg.pixelSize;
   dim3 pg(OBcur, h->nbands);
+  // the attribute belongs to the function, not to this handle: other handles (other image sizes)
+  // may have changed it since, so it is set at every launch
+  CU(cudaFuncSetAttribute(project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ((size_t) h->band_rows * N * 4)));
   project_kernel<<<pg, 256, (size_t) h->band_rows * N * 4, h->stream>>>(pp);
   CU(cudaGetLastError());
   CU(do_fft2d(N, h->d_proj, h->d_tempden, h->nbands, h->NormDen, h->d_tw_fwd, h->d_scratch, h->d_projfft, OBcur, h->stream));

@@ -43,6 +43,7 @@ struct Params // reference bioem_param after readParameters + CalculateGridsPara
   std::vector<float> angles;   // nOrient x {pos[3], quat4}
   std::vector<float> angprior; // nOrient (PRIOR_ANGLES)
   float voluang = 0.f;
+  std::vector<float> psfKernels; // USE_PSF: nCtf x N x N real-space kernels (refCTF stays empty)
   std::vector<float> refCTF;   // nCtf x N x (N/2+1) x 2
   std::vector<float> CtfParam; // nCtf x 4 {amp, phase, env, -}
   int nCtf = 0;

@@ -364,7 +364,6 @@ void read_parameters(const std::string &file, Params &p)
       fail("Input missing: please provide grid PSF ENVELOPE");
     if (!yAmp)
       fail("Input missing: please provide grid PSF AMPLITUD");
-    fail("USE_PSF: point-spread-function kernels are not on the B200 path yet (CTF mode only)");
   }
   else
   {
@@ -510,17 +509,39 @@ void make_orientations(const std::string &orientfile, Params &p)
 void make_ctf_table(Params &p)
 {
   float grids[3];
-  p.nCtf = bioem_b200_host_ctf_table(p.N, p.pixelSize, 0, p.startAmp, p.endAmp, p.nAmp, p.startPhase, p.endPhase, p.nPhase,
-                                     p.startEnv, p.endEnv, p.nEnv, nullptr, nullptr, grids);
-  if (p.nCtf <= 0)
-    fail("CTF grid is empty");
-  const size_t F = (size_t) p.N * (p.N / 2 + 1);
-  p.refCTF.assign((size_t) p.nCtf * F * 2, 0.f);
-  p.CtfParam.assign((size_t) p.nCtf * 4, 0.f);
-  const int got = bioem_b200_host_ctf_table(p.N, p.pixelSize, 0, p.startAmp, p.endAmp, p.nAmp, p.startPhase, p.endPhase,
-                                            p.nPhase, p.startEnv, p.endEnv, p.nEnv, p.refCTF.data(), p.CtfParam.data(), grids);
-  if (got != p.nCtf)
-    fail("CTF table: %d kernels built, %d expected", got, p.nCtf);
+  if (p.startAmp < 0 || p.endAmp > 1)
+    fail("PSF amplitude should be between 0 and 1. start: %lf end: %lf", (double) p.startAmp, (double) p.endAmp);
+  if (p.usepsf)
+  {
+    // kernels in real space; the library takes their r2c transform on the device (param.cpp:1466-1535)
+    p.nCtf = bioem_b200_host_psf_kernels(p.N, p.pixelSize, p.startAmp, p.endAmp, p.nAmp, p.startPhase, p.endPhase, p.nPhase,
+                                         p.startEnv, p.endEnv, p.nEnv, nullptr, nullptr, grids);
+    if (p.nCtf <= 0)
+      fail("PSF grid is empty");
+    p.psfKernels.assign((size_t) p.nCtf * p.N * p.N, 0.f);
+    p.CtfParam.assign((size_t) p.nCtf * 4, 0.f);
+    const int got = bioem_b200_host_psf_kernels(p.N, p.pixelSize, p.startAmp, p.endAmp, p.nAmp, p.startPhase, p.endPhase,
+                                                p.nPhase, p.startEnv, p.endEnv, p.nEnv, p.psfKernels.data(), p.CtfParam.data(),
+                                                grids);
+    if (got == -3)
+      fail("MAX standard deviation of envelope is larger than allowed KERNEL length");
+    if (got != p.nCtf)
+      fail("PSF table: %d kernels built, %d expected", got, p.nCtf);
+  }
+  else
+  {
+    p.nCtf = bioem_b200_host_ctf_table(p.N, p.pixelSize, 0, p.startAmp, p.endAmp, p.nAmp, p.startPhase, p.endPhase, p.nPhase,
+                                       p.startEnv, p.endEnv, p.nEnv, nullptr, nullptr, grids);
+    if (p.nCtf <= 0)
+      fail("CTF grid is empty");
+    const size_t F = (size_t) p.N * (p.N / 2 + 1);
+    p.refCTF.assign((size_t) p.nCtf * F * 2, 0.f);
+    p.CtfParam.assign((size_t) p.nCtf * 4, 0.f);
+    const int got = bioem_b200_host_ctf_table(p.N, p.pixelSize, 0, p.startAmp, p.endAmp, p.nAmp, p.startPhase, p.endPhase,
+                                              p.nPhase, p.startEnv, p.endEnv, p.nEnv, p.refCTF.data(), p.CtfParam.data(), grids);
+    if (got != p.nCtf)
+      fail("CTF table: %d kernels built, %d expected", got, p.nCtf);
+  }
   p.volu = bioem_b200_host_volu(p.voluang, p.GridSpaceCenter, p.pixelSize, p.maxDisplaceCenter, p.nAmp, grids[2], grids[1],
                                 p.sigmaPriorbctf, p.sigmaPriordefo, p.sigmaPrioramp);
 }

@@ -199,7 +199,10 @@ int main(int argc, char **argv)
     wr("maps.bin", maps.data(), maps.size() * sizeof(float));
     wr("angles.bin", par.angles.data(), par.angles.size() * sizeof(float));
     wr("ctfparam.bin", par.CtfParam.data(), (size_t) C * 4 * sizeof(float));
-    wr("refctf.bin", par.refCTF.data(), (size_t) C * par.N * (par.N / 2 + 1) * 2 * sizeof(float));
+    if (par.usepsf)
+      wr("psfkernels.bin", par.psfKernels.data(), (size_t) C * par.N * par.N * sizeof(float));
+    else
+      wr("refctf.bin", par.refCTF.data(), (size_t) C * par.N * (par.N / 2 + 1) * 2 * sizeof(float));
     const std::string meta = std::string(dump) + "/meta.txt";
     FILE *f = fopen(meta.c_str(), "w");
     if (!f)
@@ -266,7 +269,9 @@ int main(int argc, char **argv)
     bool ok = chk(bioem_b200_create(&cfg, g, &h), "create") &&
               chk(bioem_b200_upload_model(h, pts.data(), (int) pts.size(), NormDen), "upload_model") &&
               chk(bioem_b200_upload_orientations(h, par.angles.data(), O), "upload_orientations") &&
-              chk(bioem_b200_upload_ctf(h, par.refCTF.data(), par.CtfParam.data(), C), "upload_ctf") &&
+              chk(par.usepsf ? bioem_b200_upload_ctf_real(h, par.psfKernels.data(), par.CtfParam.data(), C)
+                             : bioem_b200_upload_ctf(h, par.refCTF.data(), par.CtfParam.data(), C),
+                  "upload_ctf") &&
               chk(bioem_b200_upload_particles(h, maps.data(), nMaps), "upload_particles") &&
               chk(bioem_b200_reset(h), "reset") && chk(bioem_b200_run(h, o0, o1), "run") &&
               chk(bioem_b200_download(h, parts[g].data(), cfg.writeAngles ? mine.data() : nullptr), "download");

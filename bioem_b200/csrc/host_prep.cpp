@@ -53,7 +53,7 @@ int bioem_b200_host_ctf_table(int N, float pixelSize, int usepsf, float startAmp
   if (!refCTF && !CtfParam4)
     return nTot;
   if (usepsf)
-    return -2; // PSF kernels are built on the device (bioem_b200_upload_psf, next round)
+    return -2; // point-spread functions are built in real space: bioem_b200_host_psf_kernels + upload_ctf_real
   const int nc = N / 2 + 1;
   const size_t F = (size_t) N * nc;
   std::vector<int> writer(N, -1);
@@ -102,6 +102,77 @@ int bioem_b200_host_ctf_table(int N, float pixelSize, int usepsf, float startAmp
               for (int j = 0; j < nc; j++)
                 cur[2 * ((size_t) r * nc + j)] = row[j];
         }
+      }
+    }
+  }
+  return nTot;
+}
+
+// reference param.cpp:1336-1536, USE_PSF: the kernels are defined in REAL space (radially symmetric
+// around pixel (0,0), periodic), normalised to unit sum; the reference then takes their r2c FFT
+// (param.cpp:1521) -- here that transform runs on the device (bioem_b200_upload_ctf_real).
+int bioem_b200_host_psf_kernels(int N, float pixelSize, float startAmp, float endAmp, int nAmp, float startPhase,
+                                float endPhase, int nPhase, float startEnv, float endEnv, int nEnv, float *kernels,
+                                float *CtfParam4, float *grids)
+{
+  if (N <= 0 || nAmp <= 0 || nPhase <= 0 || nEnv <= 0)
+    return -1;
+  float stepAmp = (endAmp - startAmp) / (float) nAmp;
+  float stepPhase = (endPhase - startPhase) / (float) nPhase;
+  float stepEnv = (endEnv - startEnv) / (float) nEnv;
+  if (nAmp == 1)
+    stepAmp = startAmp;
+  if (nPhase == 1)
+    stepPhase = startPhase;
+  if (nEnv == 1)
+    stepEnv = startEnv;
+  if (grids)
+  {
+    grids[0] = stepAmp;
+    grids[1] = stepPhase;
+    grids[2] = stepEnv;
+  }
+  const int nTot = nAmp * nPhase * nEnv;
+  if (!kernels && !CtfParam4)
+    return nTot;
+  // widest envelope must fit the kernel length (param.cpp:1403-1409)
+  if (sqrt(1. / ((float) nEnv * stepEnv + startEnv)) > float(N) / 2.0)
+    return -3;
+  const int nctfmax = N / 2;
+  int n = 0;
+  for (int ia = 0; ia < nAmp; ia++)
+  {
+    const float amp = (float) ia * stepAmp + startAmp;
+    for (int ip = 0; ip < nPhase; ip++)
+    {
+      const float phase = (float) ip * stepPhase + startPhase;
+      for (int ie = 0; ie < nEnv; ie++, n++)
+      {
+        const float env = (float) ie * stepEnv + startEnv;
+        if (CtfParam4)
+        {
+          CtfParam4[4 * n + 0] = amp;
+          CtfParam4[4 * n + 1] = phase;
+          CtfParam4[4 * n + 2] = env;
+          CtfParam4[4 * n + 3] = 0.f;
+        }
+        if (!kernels)
+          continue;
+        float *cur = kernels + (size_t) n * N * N;
+        float normctf = 0.f;
+        for (int i = 0; i < N; i++)
+          for (int j = 0; j < N; j++)
+          {
+            const int ri = (i < nctfmax + 1) ? i : N - i;
+            const int rj = (j < nctfmax + 1) ? j : N - j;
+            const float radsq = (float) (ri * ri + rj * rj) * pixelSize * pixelSize;
+            const float ctf = (float) (exp(-radsq * env / 2.0) * (-amp * cos(radsq * phase / 2.0) -
+                                                                  sqrtf(1 - amp * amp) * sin(radsq * phase / 2.0)));
+            cur[(size_t) i * N + j] = ctf;
+            normctf += ctf;
+          }
+        for (size_t k = 0; k < (size_t) N * N; k++)
+          cur[k] = cur[k] / normctf;
       }
     }
   }

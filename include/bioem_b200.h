@@ -97,6 +97,9 @@ int bioem_b200_upload_orientations(bioem_b200_handle h, const float *angles4, in
 /* param.refCTF (nCtf x N x (N/2+1) interleaved complex, reference param.cpp:1359) and
  * param.CtfParam (nCtf x myfloat3_t {amp, phase, env, -}) */
 int bioem_b200_upload_ctf(bioem_b200_handle h, const float *refCTF, const float *CtfParam4, int nCtf);
+/* USE_PSF: the nCtf kernels given as real-space point-spread functions (nCtf x N x N); the library
+ * takes their forward r2c transform, which the reference does on the host (param.cpp:1466-1535). */
+int bioem_b200_upload_ctf_real(bioem_b200_handle h, const float *kernels, const float *CtfParam4, int nCtf);
 /* RefMap.maps (nMaps x N x N, as read, BEFORE RefMap.precalculate): the library
  * computes sum_RefMap / sumsquare_RefMap / RefMapsFFT itself (replaces reference
  * map.cpp:557-630). */
@@ -162,6 +165,12 @@ void bioem_b200_host_defocus_to_phase(float startDefocus, float endDefocus, floa
 int bioem_b200_host_ctf_table(int N, float pixelSize, int usepsf, float startAmp, float endAmp, int nAmp,
                               float startPhase, float endPhase, int nPhase, float startEnv, float endEnv,
                               int nEnv, float *refCTF, float *CtfParam4, float *grids);
+/* param.cpp:1336-1536 with USE_PSF: real-space point-spread functions (nCtf x N x N, unit sum) for
+ * bioem_b200_upload_ctf_real; returns nCtf (kernels / CtfParam4 may be NULL to query), -3 if the
+ * widest envelope does not fit the kernel length */
+int bioem_b200_host_psf_kernels(int N, float pixelSize, float startAmp, float endAmp, int nAmp, float startPhase,
+                                float endPhase, int nPhase, float startEnv, float endEnv, int nEnv, float *kernels,
+                                float *CtfParam4, float *grids);
 /* param.cpp:1600-1607 */
 float bioem_b200_host_volu(float voluang, int GridSpaceCenter, float pixelSize, int maxDisplaceCenter,
                            int nAmp, float gridEnvelop, float gridCTF_phase, float sigmaPriorbctf,

@@ -104,17 +104,24 @@ class Prepared:
         cen_d = C.c_float(ctf.get("PRIOR_DEFOCUS_CENTER", 3.0))
         sig_a = f32(ctf.get("SIGMA_PRIOR_AMP_CTF", 0.5))
         cen_a = f32(ctf.get("PRIOR_AMP_CTF_CENTER", 0.0))
-        d0, d1, nd = ctf["CTF_DEFOCUS"]
-        b0, b1, nb = ctf["CTF_B_ENV"]
-        a0, a1, na = ctf["CTF_AMPLITUDE"]
-        p0, p1 = C.c_float(), C.c_float()
-        L.oracle_defocus_to_phase(f32(d0), f32(d1), f32(elecwavel), C.byref(p0), C.byref(p1),
-                                  C.byref(cen_d), C.byref(sig_d))
+        self.use_psf = "PSF_PHASE" in ctf
+        grids = np.zeros(3, dtype=np.float32)
+        if not self.use_psf:
+            d0, d1, nd = ctf["CTF_DEFOCUS"]
+            b0, b1, nb = ctf["CTF_B_ENV"]
+            a0, a1, na = ctf["CTF_AMPLITUDE"]
+            p0, p1 = C.c_float(), C.c_float()
+            L.oracle_defocus_to_phase(f32(d0), f32(d1), f32(elecwavel), C.byref(p0), C.byref(p1),
+                                      C.byref(cen_d), C.byref(sig_d))
+        else:  # USE_PSF: phase / envelope grids are given directly (param.cpp:330-385)
+            p0, p1, nd = ctf["PSF_PHASE"]
+            b0, b1, nb = ctf["PSF_ENVELOPE"]
+            a0, a1, na = ctf["PSF_AMPLITUDE"]
+            p0, p1 = C.c_float(p0), C.c_float(p1)
         self.C = int(na * nd * nb)
         self.refCTF = np.zeros((self.C, self.F, 2), dtype=np.float32)
         self.CtfParam = np.zeros((self.C, 3), dtype=np.float32)
-        grids = np.zeros(3, dtype=np.float32)
-        c = L.oracle_ctf_table(n, f32(case.pixel_size), 0, f32(a0), f32(a1), int(na), p0, p1,
+        c = L.oracle_ctf_table(n, f32(case.pixel_size), int(self.use_psf), f32(a0), f32(a1), int(na), p0, p1,
                                int(nd), f32(b0), f32(b1), int(nb), _fp(self.refCTF),
                                _fp(self.CtfParam), _fp(grids))
         assert c == self.C
@@ -123,7 +130,7 @@ class Prepared:
         voluang = L.oracle_voluang_list(self.O, f32(priorMod))
         volu = L.oracle_volu(voluang, case.grid_space, f32(case.pixel_size), case.max_disp,
                              int(na), grids[2], grids[1], sig_b, sig_d, sig_a)
-        self.cfg = OracleCfg(n, case.max_disp, case.grid_space, case.write_angles, 0, 1, 0, 0,
+        self.cfg = OracleCfg(n, case.max_disp, case.grid_space, case.write_angles, int(self.use_psf), 1, 0, 0,
                              f32(case.pixel_size), f32(n * n), volu, sig_b, sig_d, cen_d, sig_a,
                              cen_a)
         self.pts = np.ascontiguousarray(model, dtype=np.float32).copy()
