@@ -564,8 +564,11 @@ static int ensure_batch(bioem_b200_context *h)
     return BIOEM_B200_OK;
   const int N = h->N;
   const size_t mapbytes = h->map4 * sizeof(float4);
-  // conv spectra of one batch should stay L2-resident (126 MB) when many images reuse them
-  size_t budget = (h->M >= 64) ? ((size_t) 96 << 20) : ((size_t) 1 << 30);
+  // Orientations per batch: the conv spectra of a batch live in HBM (1 GB budget); what has to stay
+  // in L2 is only the group of orientations the resident CTAs are working on (CTAs are numbered
+  // image-fastest, so all images pass over one group before the next), i.e. a few MB.  Measured on
+  // cfg2: 15 orientations per launch 18.93, 60: 19.21, 150: 19.26 M likelihoods/s (fewer launch tails).
+  size_t budget = (size_t) 1 << 30;
   if (getenv("BIOEM_B200_CONV_MB"))
     budget = (size_t) atol(getenv("BIOEM_B200_CONV_MB")) << 20;
   long ob = (long) (budget / (mapbytes * (size_t) h->C));
@@ -580,7 +583,11 @@ static int ensure_batch(bioem_b200_context *h)
   if (getenv("BIOEM_B200_OG"))
     og = std::max(1, atoi(getenv("BIOEM_B200_OG")));
   h->OG = og;
-  const size_t band_budget = 96 * 1024;
+  // bands of image rows per projection CTA: small bands = many CTAs (an orientation batch is only
+  // ~15 images), at the price of every warp skipping more model points that miss its rows
+  size_t band_budget = 12 * 1024;
+  if (getenv("BIOEM_B200_BAND_KB"))
+    band_budget = (size_t) atol(getenv("BIOEM_B200_BAND_KB")) * 1024;
   h->nbands = (int) (((size_t) N * N * 4 + band_budget - 1) / band_budget);
   h->band_rows = (N + h->nbands - 1) / h->nbands;
   h->nbands = (N + h->band_rows - 1) / h->band_rows;
