@@ -44,11 +44,12 @@ WORKLOADS = {
 }
 
 
-def _traffic(kernel: str):
-    """dram bytes per launch of the dominant kernel from the committed ncu capture (or None)."""
+def _traffic(kernel: str, likelihoods_per_launch: float):
+    """dram bytes per (average) launch of the dominant kernel, from the committed ncu capture
+    (bytes per likelihood x likelihoods per launch), or None."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     try:
-        return int(json.load(open(p))[kernel]["dram_bytes_per_launch"])
+        return int(float(json.load(open(p))[kernel]["dram_bytes_per_likelihood"]) * likelihoods_per_launch)
     except Exception:
         return None
 
@@ -244,7 +245,7 @@ def run_ours(args):
             ach = per_rank_lik * 8.0 * F / (lik_ms / 1e3) / 1e9
             flop = 2.5 * N * N * np.log2(N * N)
             roof = {"bound": "hbm", "achieved": round(ach, 1), "peak": hbm_peak, "unit": "GB/s",
-                    "frac": round(ach / hbm_peak, 4), "traffic": _traffic(f"likelihood_kernel<{N}>"),
+                    "frac": round(ach / hbm_peak, 4), "traffic": _traffic(f"likelihood_kernel<{N}>", per_rank_lik / lik_launches),
                     "peak_source": peak_src,
                     "kernel": f"likelihood_kernel<{N}>", "launches": lik_launches,
                     "avg_launch_ms": round(lik_ms / lik_launches, 3),
