@@ -764,6 +764,7 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
   __shared__ float s_ws[NPEND][NWARP];
   __shared__ float s_wv[NPEND][NWARP];
   __shared__ int s_poc[NPEND];
+  __shared__ unsigned long long s_mbar; // closing barrier of a likelihood (one arrival per warp)
   __shared__ BookState s_bk;
 
   const int nw = p.nw, nwp = p.nwp;
@@ -787,8 +788,11 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
         RS[nw] = (unsigned char) (j * R1 + k1); // padding row of an odd window: any valid slot
     }
   }
+  const unsigned mbar_addr = (unsigned) __cvta_generic_to_shared(&s_mbar);
+  unsigned mbar_parity = 0;
   if (tid == 0)
   {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar_addr), "r"(NWARP) : "memory");
     s_bk.Const = kMinProb;
     s_bk.Total = 0.0;
     s_bk.lpf = 0.f;
@@ -1013,12 +1017,8 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
     }
     __syncwarp();
   };
-  // Row tasks (KC row pairs each) are dealt round robin, so the last round is not full: the warps
-  // without a task in it run the first radix pass of their first column chunk of the NEXT
-  // likelihood before the closing barrier instead of idling (its operands do not depend on Y).
-  const int npairs_all = nwp / 2;
-  const int row_rounds = (npairs_all + NWARP * KC - 1) / (NWARP * KC);
-  const bool short_rows = warp * KC + (row_rounds - 1) * NWARP * KC >= npairs_all; // no task in the last round
+  // pass 1 of this warp's first column chunk was already run behind the closing barrier of the
+  // previous likelihood
   bool pre_done = false;
 
   for (int ol = o_lo; ol < o_hi; ol++)
@@ -1212,12 +1212,30 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
         s_wc[slot][warp] = cand;
         s_ws[slot][warp] = S;
       }
-      if (short_rows && warp < NCH && oc + 1 < o_hi * p.C)
+      // Closing barrier, split: arrive (this warp is done with Y, its ring entry is written), then
+      // -- instead of idling until the slowest warp is through its row tasks -- run the first radix
+      // pass of this warp's first column chunk of the NEXT likelihood (it needs neither Y nor the
+      // other warps), and only then wait.  Y may be overwritten after the wait.
+      __syncwarp();
+      if (lane == 0)
+        asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(mbar_addr) : "memory");
+      if (warp < NCH && oc + 1 < o_hi * p.C)
       {
         col1(warp, conv + L::MAP4); // the next conv spectrum of the batch follows this one
         pre_done = true;
       }
-      __syncthreads(); // Y consumed (the next column pass may overwrite it), ring entry complete
+      {
+        unsigned done;
+        do
+        {
+          asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2;\n\t"
+                       "selp.u32 %0, 1, 0, p;\n\t}"
+                       : "=r"(done)
+                       : "r"(mbar_addr), "r"(mbar_parity)
+                       : "memory");
+        } while (!done);
+        mbar_parity ^= 1u;
+      }
       slot++;
       if (slot == NPEND || (p.angles && c == p.C - 1))
       {
