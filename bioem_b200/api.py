@@ -46,7 +46,8 @@ EXPORTS = [
     "bioem_b200_last_error", "bioem_b200_version", "bioem_b200_device_count",
     "bioem_b200_supported_size", "bioem_b200_create", "bioem_b200_destroy",
     "bioem_b200_upload_model", "bioem_b200_upload_orientations", "bioem_b200_upload_ctf",
-    "bioem_b200_upload_ctf_real", "bioem_b200_upload_particles", "bioem_b200_upload_particles_fft",
+    "bioem_b200_upload_ctf_real", "bioem_b200_upload_particles", "bioem_b200_upload_particles_mrc",
+    "bioem_b200_upload_particles_fft",
     "bioem_b200_reset",
     "bioem_b200_run", "bioem_b200_synchronize", "bioem_b200_download",
     "bioem_b200_partial_bytes", "bioem_b200_export_partial", "bioem_b200_import_partials",
@@ -88,6 +89,7 @@ def lib():
     L.bioem_b200_upload_ctf.argtypes = [vp, fp, fp, C.c_int]
     L.bioem_b200_upload_ctf_real.argtypes = [vp, fp, fp, C.c_int]
     L.bioem_b200_upload_particles.argtypes = [vp, fp, C.c_int]
+    L.bioem_b200_upload_particles_mrc.argtypes = [vp, fp, C.c_int, C.c_int]
     L.bioem_b200_upload_particles_fft.argtypes = [vp, fp, fp, fp, C.c_int]
     L.bioem_b200_reset.argtypes = [vp]
     L.bioem_b200_run.argtypes = [vp, C.c_int, C.c_int]
@@ -268,6 +270,13 @@ class Engine:
         m = np.ascontiguousarray(maps, dtype=np.float32)
         self.M = m.shape[0]
         _chk(lib().bioem_b200_upload_particles(self._h, _fp(m), self.M), "upload_particles")
+
+    def upload_particles_mrc(self, raw: np.ndarray, normalise: bool = True):
+        """raw: [M, nr, nc] images in MRC file order (before the reader's transposition)."""
+        r = np.ascontiguousarray(raw, dtype=np.float32)
+        self.M = r.shape[0]
+        _chk(lib().bioem_b200_upload_particles_mrc(self._h, _fp(r), self.M, int(normalise)),
+             "upload_particles_mrc")
 
     def upload_particles_fft(self, fft: np.ndarray, s: np.ndarray, ss: np.ndarray):
         f = np.ascontiguousarray(fft, dtype=np.float32)

@@ -560,6 +560,46 @@ int bioem_b200_upload_particles(bioem_b200_handle h, const float *maps, int M)
   return BIOEM_B200_OK;
 }
 
+int bioem_b200_upload_particles_mrc(bioem_b200_handle h, const float *raw, int M, int normalise)
+{
+  if (!h || !raw || M <= 0)
+    return fail(BIOEM_B200_ERR_INVALID, "upload_particles_mrc: bad argument");
+  CU(cudaSetDevice(h->device));
+  int rc = set_particle_count(h, M);
+  if (rc)
+    return rc;
+  const int N = h->N;
+  const size_t n2 = (size_t) N * N;
+  const int chunk = (int) std::max<size_t>(1, std::min<size_t>((size_t) M, ((size_t) 1 << 29) / (n2 * 4)));
+  float *d_raw = nullptr, *d_img = nullptr, *d_mean = nullptr, *d_dev = nullptr;
+  float2 *d_scr = nullptr;
+  CU(cudaMallocAsync((void **) &d_raw, sizeof(float) * n2 * chunk, h->stream));
+  CU(cudaMallocAsync((void **) &d_img, sizeof(float) * n2 * chunk, h->stream));
+  CU(cudaMallocAsync((void **) &d_mean, sizeof(float) * chunk, h->stream));
+  CU(cudaMallocAsync((void **) &d_dev, sizeof(float) * chunk, h->stream));
+  CU(cudaMallocAsync((void **) &d_scr, sizeof(float2) * (size_t) N * (N / 2 + 1) * chunk, h->stream));
+  for (int m0 = 0; m0 < M; m0 += chunk)
+  {
+    const int mc = std::min(chunk, M - m0);
+    CU(cudaMemcpyAsync(d_raw, raw + (size_t) m0 * n2, sizeof(float) * n2 * mc, cudaMemcpyHostToDevice, h->stream));
+    if (normalise)
+      mrc_stats_kernel<<<(mc + 63) / 64, 64, 0, h->stream>>>(d_raw, (int) n2, mc, d_mean, d_dev);
+    dim3 tg((N + 31) / 32, (N + 31) / 32, mc);
+    mrc_transpose_kernel<<<tg, dim3(32, 8), 0, h->stream>>>(d_raw, d_mean, d_dev, N, normalise, d_img);
+    image_sums_kernel<<<(mc + 63) / 64, 64, 0, h->stream>>>(d_img, (int) n2, mc, h->d_sumRef + m0, h->d_sumsqRef + m0);
+    CU(cudaGetLastError());
+    CU(do_fft2d(N, d_img, nullptr, 0, 0.f, h->d_tw_fwd, d_scr, h->d_refs + (size_t) m0 * h->map4, mc, h->stream));
+    h->launches += 5;
+    CU(cudaStreamSynchronize(h->stream));
+  }
+  dfree(h, d_raw);
+  dfree(h, d_img);
+  dfree(h, d_mean);
+  dfree(h, d_dev);
+  dfree(h, d_scr);
+  return BIOEM_B200_OK;
+}
+
 int bioem_b200_upload_particles_fft(bioem_b200_handle h, const float *fft, const float *sum, const float *sumsq, int M)
 {
   if (!h || !fft || !sum || !sumsq || M <= 0)

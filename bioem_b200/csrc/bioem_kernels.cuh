@@ -486,6 +486,57 @@ __global__ void image_sums_kernel(const float *__restrict__ imgs, int n2, int M,
   sumsq[m] = ss;
 }
 
+// MRC particle ingest (reference map.cpp:811-845): per-image mean and deviation accumulated in
+// FILE order with float accumulators (sequential, like the reader's loop), then the image is
+// stored transposed (maps[i*N + j] = file[j*N + i]) and, unless NO_MAP_NORM, scaled to zero mean
+// / unit deviation with the reference's expression  x / st2 - st / st2.
+__global__ void mrc_stats_kernel(const float *__restrict__ raw, int n2, int M, float *__restrict__ mean,
+                                 float *__restrict__ dev)
+{
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M)
+    return;
+  const float *p = raw + (size_t) m * n2;
+  float st = 0.f, st2 = 0.f;
+  for (int i = 0; i < n2; i++)
+  {
+    const float v = p[i];
+    st = __fadd_rn(st, v);
+    st2 = __fadd_rn(st2, __fmul_rn(v, v));
+  }
+  st = __fdiv_rn(st, (float) n2);
+  st2 = __fsqrt_rn(__fsub_rn(__fdiv_rn(st2, (float) n2), __fmul_rn(st, st)));
+  mean[m] = st;
+  dev[m] = st2;
+}
+
+__global__ void mrc_transpose_kernel(const float *__restrict__ raw, const float *__restrict__ mean,
+                                     const float *__restrict__ dev, int N, int normalise, float *__restrict__ maps)
+{
+  __shared__ float tile[32][33];
+  const int m = blockIdx.z;
+  const float *src = raw + (size_t) m * N * N;
+  float *dst = maps + (size_t) m * N * N;
+  const int j0 = blockIdx.y * 32, i0 = blockIdx.x * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y)
+  {
+    const int j = j0 + r, i = i0 + threadIdx.x;
+    if (j < N && i < N)
+      tile[r][threadIdx.x] = src[(size_t) j * N + i];
+  }
+  __syncthreads();
+  const float st = normalise ? mean[m] : 0.f, st2 = normalise ? dev[m] : 1.f;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y)
+  {
+    const int i = i0 + r, j = j0 + threadIdx.x;
+    if (i < N && j < N)
+    {
+      const float v = tile[threadIdx.x][r];
+      dst[(size_t) i * N + j] = normalise ? __fsub_rn(__fdiv_rn(v, st2), __fdiv_rn(st, st2)) : v;
+    }
+  }
+}
+
 #endif // BIOEM_LIK_ONLY
 
 // ===========================================================================

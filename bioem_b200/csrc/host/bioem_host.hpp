@@ -56,7 +56,11 @@ void read_parameters(const std::string &file, Params &p);                  // pa
 void make_orientations(const std::string &orientfile, Params &p);          // param.cpp:988-1334
 void make_ctf_table(Params &p);                                            // param.cpp:1336-1620 via the C ABI
 void read_model(const Options &o, const Params &p, std::vector<bioem_b200_model_point> &pts, float &NormDen);
-void read_particles(const Options &o, const Params &p, std::vector<float> &maps, int &nMaps);
+// maps: nMaps x N x N.  For MRC stacks (rawMRC = true) the images are left exactly as they lie in the
+// file; the library transposes / normalises them on the device (bioem_b200_upload_particles_mrc).
+void read_particles(const Options &o, const Params &p, std::vector<float> &maps, int &nMaps, bool &rawMRC);
+// what the reference's MRC reader does to a raw stack, on the host (for --DumpMaps and the test hook)
+void mrc_host_ingest(const Params &p, std::vector<float> &maps, int nMaps);
 void write_outputs(const Options &o, const Params &p, const bioem_b200_config &cfg,
                    const std::vector<bioem_b200_prob_map> &pm, const std::vector<bioem_b200_prob_angle> &pa, int nMaps);
 

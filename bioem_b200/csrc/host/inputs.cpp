@@ -801,26 +801,35 @@ static void append_mrc_stack(const std::string &file, const Params &p, std::vect
   if (fseek(f, 1024 + h.nsymbt, SEEK_SET) != 0)
     fail("Converting Data: %s", name);
   const size_t n2 = (size_t) p.N * p.N;
-  std::vector<float> img(n2);
   maps.resize((size_t) (nMaps + h.ns) * n2);
-  for (int s = 0; s < h.ns; s++)
-  {
-    read_mrc_floats(f, img.data(), n2, h.swap, name);
-    float *dst = maps.data() + (size_t) (nMaps + s) * n2;
-    for (int j = 0; j < h.nr; j++)
-      for (int i = 0; i < h.nc; i++)
-        dst[(size_t) i * p.N + j] = img[(size_t) j * h.nc + i];
-    if (!p.notnormmap)
-      bioem_b200_host_normalise_map(dst, p.N); // statistics accumulated in file order, like the reference
-  }
+  read_mrc_floats(f, maps.data() + (size_t) nMaps * n2, n2 * h.ns, h.swap, name); // file order, untouched
   nMaps += h.ns;
   fclose(f);
 }
 
-void read_particles(const Options &o, const Params &p, std::vector<float> &maps, int &nMaps)
+// image stored transposed (maps[i*N + j] with the file running j-outer / i-inner), then zero mean /
+// unit deviation with float accumulators in file order unless NO_MAP_NORM (map.cpp:811-845)
+void mrc_host_ingest(const Params &p, std::vector<float> &maps, int nMaps)
+{
+  const size_t n2 = (size_t) p.N * p.N;
+  std::vector<float> img(n2);
+  for (int s = 0; s < nMaps; s++)
+  {
+    float *dst = maps.data() + (size_t) s * n2;
+    std::copy(dst, dst + n2, img.begin());
+    for (int j = 0; j < p.N; j++)
+      for (int i = 0; i < p.N; i++)
+        dst[(size_t) i * p.N + j] = img[(size_t) j * p.N + i];
+    if (!p.notnormmap)
+      bioem_b200_host_normalise_map(dst, p.N);
+  }
+}
+
+void read_particles(const Options &o, const Params &p, std::vector<float> &maps, int &nMaps, bool &rawMRC)
 {
   maps.clear();
   nMaps = 0;
+  rawMRC = false;
   const size_t n2 = (size_t) p.N * p.N;
   if (o.loadMapDump)
   {
@@ -861,6 +870,7 @@ void read_particles(const Options &o, const Params &p, std::vector<float> &maps,
     }
     else
       append_mrc_stack(o.particlesfile, p, maps, nMaps);
+    rawMRC = true;
     std::cout << "Particle Maps read from MRC\n";
   }
   else
@@ -915,15 +925,6 @@ void read_particles(const Options &o, const Params &p, std::vector<float> &maps,
   }
   if (nMaps <= 0)
     fail("No particle images read from %s", o.particlesfile.c_str());
-  if (o.dumpMaps)
-  {
-    FILE *f = fopen("maps.dump", "wb");
-    if (!f)
-      fail("Opening file: maps.dump");
-    fwrite(&nMaps, sizeof(int), 1, f);
-    fwrite(maps.data(), sizeof(float), maps.size(), f);
-    fclose(f);
-  }
   if (getenv("BIOEM_DEBUG_NMAPS")) // the reference's debugging knob (map.cpp:545-548)
   {
     const int cap = atoi(getenv("BIOEM_DEBUG_NMAPS"));
@@ -932,6 +933,20 @@ void read_particles(const Options &o, const Params &p, std::vector<float> &maps,
       nMaps = cap;
       maps.resize((size_t) nMaps * n2);
     }
+  }
+  if (o.dumpMaps)
+  {
+    if (rawMRC) // the dump holds the maps as the reference keeps them in memory
+    {
+      mrc_host_ingest(p, maps, nMaps);
+      rawMRC = false;
+    }
+    FILE *f = fopen("maps.dump", "wb");
+    if (!f)
+      fail("Opening file: maps.dump");
+    fwrite(&nMaps, sizeof(int), 1, f);
+    fwrite(maps.data(), sizeof(float), maps.size(), f);
+    fclose(f);
   }
   std::cout << "Total Number of particles: " << nMaps << "\n+++++++++++++++++++++++++++++++++++++++++++ \n";
 }

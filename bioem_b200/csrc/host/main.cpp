@@ -169,7 +169,8 @@ int main(int argc, char **argv)
   read_parameters(opt.inputfile, par);
   std::vector<float> maps;
   int nMaps = 0;
-  read_particles(opt, par, maps, nMaps);
+  bool rawMRC = false;
+  read_particles(opt, par, maps, nMaps, rawMRC);
   std::vector<bioem_b200_model_point> pts;
   float NormDen = 0.f;
   read_model(opt, par, pts, NormDen);
@@ -195,6 +196,8 @@ int main(int argc, char **argv)
         fail("cannot write %s", path.c_str());
       fclose(f);
     };
+    if (rawMRC)
+      mrc_host_ingest(par, maps, nMaps);
     wr("points.bin", pts.data(), pts.size() * sizeof(pts[0]));
     wr("maps.bin", maps.data(), maps.size() * sizeof(float));
     wr("angles.bin", par.angles.data(), par.angles.size() * sizeof(float));
@@ -272,7 +275,9 @@ int main(int argc, char **argv)
               chk(par.usepsf ? bioem_b200_upload_ctf_real(h, par.psfKernels.data(), par.CtfParam.data(), C)
                              : bioem_b200_upload_ctf(h, par.refCTF.data(), par.CtfParam.data(), C),
                   "upload_ctf") &&
-              chk(bioem_b200_upload_particles(h, maps.data(), nMaps), "upload_particles") &&
+              chk(rawMRC ? bioem_b200_upload_particles_mrc(h, maps.data(), nMaps, par.notnormmap ? 0 : 1)
+                         : bioem_b200_upload_particles(h, maps.data(), nMaps),
+                  "upload_particles") &&
               chk(bioem_b200_reset(h), "reset") && chk(bioem_b200_run(h, o0, o1), "run") &&
               chk(bioem_b200_download(h, parts[g].data(), cfg.writeAngles ? mine.data() : nullptr), "download");
     if (ok && cfg.writeAngles) // rows of this block only; blocks are disjoint

@@ -104,6 +104,11 @@ int bioem_b200_upload_ctf_real(bioem_b200_handle h, const float *kernels, const 
  * computes sum_RefMap / sumsquare_RefMap / RefMapsFFT itself (replaces reference
  * map.cpp:557-630). */
 int bioem_b200_upload_particles(bioem_b200_handle h, const float *maps, int nMaps);
+/* the images of an MRC mode-2 stack exactly as they lie in the file (nMaps x nr x nc floats, column
+ * index fastest): the library does what the reference's reader does on the host -- transposition
+ * and, if normalise != 0 (no NO_MAP_NORM), zero mean / unit deviation with float accumulators in
+ * file order (map.cpp:811-845) -- then the precalculation above. */
+int bioem_b200_upload_particles_mrc(bioem_b200_handle h, const float *raw, int nMaps, int normalise);
 /* alternative: the caller already ran RefMap.precalculate (RefMapsFFT nMaps x N x
  * (N/2+1) complex, sum_RefMap, sumsquare_RefMap) */
 int bioem_b200_upload_particles_fft(bioem_b200_handle h, const float *RefMapsFFT, const float *sum_RefMap,

@@ -250,3 +250,28 @@ def test_recovers_planted_parameters(setups):
     pm, _ = eng.download()
     hit = sum(int(pm[m]["orient"] == cd.truth[m, 0]) for m in range(P.M))
     assert hit >= P.M - 2, (pm["orient"], cd.truth[:, 0])
+
+
+def test_mrc_ingest_on_device_matches_host_reader(setups):
+    """§8 f2: an MRC stack handed over in file order (upload_particles_mrc: transposition and
+    normalisation with float accumulators in file order ON THE DEVICE, reference map.cpp:811-845)
+    gives bit for bit the particle sums and spectra of the host-side reader path."""
+    cd, hi, parts, eng, P = setups("toy64")
+    raw = np.ascontiguousarray(np.transpose(cd.particles, (0, 2, 1)))  # what the MRC file holds
+    e2 = api.Engine(hi.cfg)
+    e2.upload_model(hi.points, hi.NormDen)
+    e2.upload_orientations(hi.angles)
+    e2.upload_ctf(hi.refCTF, hi.CtfParam)
+    e2.upload_particles_mrc(raw, True)
+    for m in range(P.M):
+        fa, sa, ssa = eng.debug_particle(m)
+        fb, sb, ssb = e2.debug_particle(m)
+        assert sa == sb and ssa == ssb
+        assert np.array_equal(fa, fb)
+    e2.run()
+    eng.reset()
+    eng.run()
+    a, _ = eng.download()
+    b, _ = e2.download()
+    e2.close()
+    assert a.tobytes() == b.tobytes()
