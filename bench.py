@@ -261,7 +261,7 @@ def run_ours(args):
                                    f"{N}x{N}, DISPLACE_CENTER {case.max_disp} {case.grid_space}",
                        "likelihoods_per_step": likelihoods_step,
                        "parallelism": f"orientation-sharded x{world}" if world > 1 else "single GPU",
-                       "l2": "inputs larger than L2 (particle spectra 201 MB + per-batch conv spectra 97 MB)"},
+                       "l2": "inputs larger than L2 (particle spectra 202 MB re-streamed per orientation group + 1.07 GB of conv spectra per launch)"},
             "clocks": clocks,
             "e2e": {"value": round(e2e_val, 1) if e2e_val else None, "unit": "likelihoods/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(out_maps.nbytes), "steps": e2e_steps},
