@@ -110,7 +110,8 @@ def build_case(name_or_case, outdir: str | None = None, n_particles: int | None 
                                             else "particles.txt"))
         synth.write_model_text(paths["model"], model)
         synth.write_param_file(paths["param"], c.n_pixels, c.pixel_size, c.max_disp, c.grid_space,
-                               c.ctf, True, c.write_angles, extra=["USE_PSF"] if c.use_psf else None)
+                               c.ctf, True, c.write_angles,
+                               extra=["USE_PSF", "WRITE_CTF_PARAM 1"] if c.use_psf else None)
         synth.write_orientation_list(paths["orient"], quats)
         if c.particle_format == "mrc":
             synth.write_particles_mrc(paths["particles"], imgs)

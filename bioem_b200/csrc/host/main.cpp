@@ -107,6 +107,14 @@ void write_outputs(const Options &o, const Params &p, const bioem_b200_config &c
       out << c[1] << " [1/A²] " << c[2] << " [1/A²] ";
     out << r.max_prob_cent_x << " [pix] " << r.max_prob_cent_y << " [pix] " << r.max_prob_norm << " [] " << r.max_prob_mu
         << " [] \n";
+    if (p.writeCTF && p.usepsf)
+    {
+      // PSF parameters of the maximum converted back to CTF defocus / B-envelope (bioem.cpp:1215-1232)
+      const float denomi = c[1] * c[1] + c[2] * c[2];
+      out << "RefMap: " << m << " CTFMaxParam: ";
+      out << 2 * M_PI * c[1] / denomi / p.elecwavel * 0.0001 << " [micro-m] ";
+      out << 4 * M_PI * M_PI * c[2] / denomi << " [A²] \n";
+    }
 
     if (cfg.writeAngles)
     {
