@@ -656,7 +656,7 @@ static int ensure_batch(bioem_b200_context *h)
   h->OG = og;
   // bands of image rows per projection CTA: small bands = many CTAs (an orientation batch is only
   // ~15 images), at the price of every warp skipping more model points that miss its rows
-  size_t band_budget = 12 * 1024;
+  size_t band_budget = 24 * 1024;
   if (getenv("BIOEM_B200_BAND_KB"))
     band_budget = (size_t) atol(getenv("BIOEM_B200_BAND_KB")) * 1024;
   h->nbands = (int) (((size_t) N * N * 4 + band_budget - 1) / band_budget);

@@ -231,62 +231,83 @@ __global__ void __launch_bounds__(256) project_kernel(ProjParams p)
   const float half = __fdiv_rn((float) N, 2.0f);
   float td = 0.f; // per-lane share of tempden
   int nskip = 0;
-  for (int n = 0; n < p.A; n++)
+  // Model points are taken in tiles: the CTA's threads rotate a tile once (pixel the point lands on,
+  // radius, density -> shared memory), then every warp walks the tile IN ORDER and adds the points
+  // that touch its rows.  (Rotating inside the walk made all warps of all bands repeat it.)
+  constexpr int PT = 1024;
+  __shared__ int4 s_pt[PT]; // i, j, radius bits, density bits; i = INT_MIN: out of frame
+  for (int n0 = 0; n0 < p.A; n0 += PT)
   {
-    const float4 pt = __ldg(&p.xyzr[n]);
-    const float den = __ldg(&p.dens[n]);
-    const float rx = __fadd_rn(__fadd_rn(__fadd_rn(0.f, __fmul_rn(m00, pt.x)), __fmul_rn(m01, pt.y)), __fmul_rn(m02, pt.z));
-    const float ry = __fadd_rn(__fadd_rn(__fadd_rn(0.f, __fmul_rn(m10, pt.x)), __fmul_rn(m11, pt.y)), __fmul_rn(m12, pt.z));
-    int i = (int) floorf(__fadd_rn(__fadd_rn(__fdiv_rn(rx, px), half), 0.5f));
-    int j = (int) floorf(__fadd_rn(__fadd_rn(__fdiv_rn(ry, px), half), 0.5f));
-    const float radius = pt.w;
-    if (radius <= px)
+    const int nt = min(PT, p.A - n0);
+    for (int k = tid; k < nt; k += blockDim.x)
     {
-      if (i < 0 || j < 0 || i >= N || j >= N)
+      const float4 pt = __ldg(&p.xyzr[n0 + k]);
+      const float den = __ldg(&p.dens[n0 + k]);
+      const float rx = __fadd_rn(__fadd_rn(__fadd_rn(0.f, __fmul_rn(m00, pt.x)), __fmul_rn(m01, pt.y)), __fmul_rn(m02, pt.z));
+      const float ry = __fadd_rn(__fadd_rn(__fadd_rn(0.f, __fmul_rn(m10, pt.x)), __fmul_rn(m11, pt.y)), __fmul_rn(m12, pt.z));
+      int i = (int) floorf(__fadd_rn(__fadd_rn(__fdiv_rn(rx, px), half), 0.5f));
+      int j = (int) floorf(__fadd_rn(__fadd_rn(__fdiv_rn(ry, px), half), 0.5f));
+      const float radius = pt.w;
+      bool skip;
+      if (radius <= px)
+        skip = i < 0 || j < 0 || i >= N || j >= N;
+      else
       {
-        nskip++;
-        continue;
+        i -= p.shiftX;
+        j -= p.shiftY;
+        const int irad = (int) __fdiv_rn(radius, px) + 1;
+        skip = i < irad || j < irad || i >= N - irad || j >= N - irad;
       }
-      if (i >= wr0 && i < wr1 && lane == 0)
-      {
-        band[(i - r0) * N + j] = __fadd_rn(band[(i - r0) * N + j], den);
-        td = __fadd_rn(td, den);
-      }
+      s_pt[k] = make_int4(skip ? (int) 0x80000000 : i, j, __float_as_int(radius), __float_as_int(den));
     }
-    else
+    __syncthreads();
+    for (int k = 0; k < nt; k++)
     {
-      i -= p.shiftX;
-      j -= p.shiftY;
-      const int irad = (int) __fdiv_rn(radius, px) + 1;
-      if (i < irad || j < irad || i >= N - irad || j >= N - irad)
+      const int4 e = s_pt[k];
+      const int i = e.x, j = e.y;
+      if (i == (int) 0x80000000)
       {
         nskip++;
         continue;
       }
-      if (i + irad < wr0 || i - irad >= wr1)
-        continue;
-      const float rad2 = __fmul_rn(radius, radius);
-      const int S = 2 * irad + 1;
-      const double denom = 4 * 3.14159265358979323846 * (double) radius * (double) rad2;
-      for (int idx = lane; idx < S * S; idx += 32)
+      const float radius = __int_as_float(e.z), den = __int_as_float(e.w);
+      if (radius <= px)
       {
-        const int di = idx / S - irad, dj = idx % S - irad;
-        const int ii = i + di, jj = j + dj;
-        if (ii < wr0 || ii >= wr1)
-          continue;
-        // dist = ((float)(di)*di + dj*dj) * px * px
-        const float dist = __fmul_rn(__fmul_rn(__fadd_rn(__fmul_rn((float) di, (float) di), (float) (dj * dj)), px), px);
-        if (dist < rad2)
+        if (i >= wr0 && i < wr1 && lane == 0)
         {
-          const float num = __fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(px, px), 2.f), sqrtf(__fsub_rn(rad2, dist))), den), 3.f);
-          const double w = (double) num / denom;
-          float *px_ = &band[(ii - r0) * N + jj];
-          *px_ = (float) ((double) *px_ + w);
-          td = (float) ((double) td + w);
+          band[(i - r0) * N + j] = __fadd_rn(band[(i - r0) * N + j], den);
+          td = __fadd_rn(td, den);
         }
       }
+      else
+      {
+        const int irad = (int) __fdiv_rn(radius, px) + 1;
+        if (i + irad < wr0 || i - irad >= wr1)
+          continue;
+        const float rad2 = __fmul_rn(radius, radius);
+        const int S = 2 * irad + 1;
+        const double denom = 4 * 3.14159265358979323846 * (double) radius * (double) rad2;
+        for (int idx = lane; idx < S * S; idx += 32)
+        {
+          const int di = idx / S - irad, dj = idx % S - irad;
+          const int ii = i + di, jj = j + dj;
+          if (ii < wr0 || ii >= wr1)
+            continue;
+          // dist = ((float)(di)*di + dj*dj) * px * px
+          const float dist = __fmul_rn(__fmul_rn(__fadd_rn(__fmul_rn((float) di, (float) di), (float) (dj * dj)), px), px);
+          if (dist < rad2)
+          {
+            const float num = __fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(px, px), 2.f), sqrtf(__fsub_rn(rad2, dist))), den), 3.f);
+            const double w = (double) num / denom;
+            float *px_ = &band[(ii - r0) * N + jj];
+            *px_ = (float) ((double) *px_ + w);
+            td = (float) ((double) td + w);
+          }
+        }
+        __syncwarp();
+      }
     }
-    __syncwarp();
+    __syncthreads();
   }
   __syncthreads();
   float *out = p.proj + (size_t) ob * N * N + (size_t) r0 * N;
