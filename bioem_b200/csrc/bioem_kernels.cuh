@@ -802,13 +802,15 @@ struct BookState
 //   * row pass, same structure: two real rows per complex transform, through the same tile,
 //   * the displacement-dependent factor of the analytic log-posterior (firstele, FP32,
 //     reference operation order, two displacements per packed instruction) straight out of
-//     the FFT registers into the consumed row slots; min firstele (<=> max logpro) per CTA,
-//   * sum of exp over the window relative to that minimum, and the displacements whose
-//     firstele is within a few ulps of it (they can share the float-narrowed logpro; the
-//     reference keeps the FIRST of them, bioem_algorithm.h:84-96),
-//   * the image's running (Constoadd, Total, arg-max) updated by one thread.
-// All butterflies run on packed FP32x2 instructions.  Three CTA-wide barriers per
-// likelihood; no correlation map ever leaves the SM.
+//     the FFT registers; every thread keeps an ONLINE (min firstele <=> max logpro, its
+//     enumeration index and correlation value, sum of exp relative to that minimum, re-based
+//     when the minimum moves); warp shuffles combine the lanes into one ring entry per warp,
+//   * the bookkeeping (double-precision log, float narrowing, first-of-ties rule over the
+//     near-minimum candidates, log-sum-exp fold into the image's running state) is deferred:
+//     warp 0 does it for up to 32 likelihoods at once, one per lane.
+// All butterflies run on packed FP32x2 instructions.  Per likelihood one CTA barrier (columns
+// -> rows) and one split-phase mbarrier (rows -> next columns: arrive, run the first radix pass
+// of the next likelihood's first chunk, wait); no correlation map ever leaves the SM.
 // ===========================================================================
 template <int N, int W>
 __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXREG) likelihood_kernel(LikParams p)
