@@ -55,6 +55,9 @@ CASES = {
     "toy32": Case("toy32", 32, 1.5, 60, 3, 576, 24, CFG1_CTF, 4, 1, write_angles=3,
                   model_sigma=5.0, model_rmax=12.0),
     "toy32psf": Case("toy32psf", 32, 1.5, 60, 3, 576, 16, PSF_GRID, 4, 1, model_sigma=5.0, model_rmax=12.0),
+    # edge windows: a single displacement, and the largest window the image allows
+    "toy32d0": Case("toy32d0", 32, 1.5, 60, 3, 576, 12, CFG1_CTF, 0, 1, model_sigma=5.0, model_rmax=12.0),
+    "toy32full": Case("toy32full", 32, 1.5, 60, 3, 576, 6, CFG1_CTF, 15, 1, model_sigma=5.0, model_rmax=12.0),
     "toy36g2": Case("toy36g2", 36, 1.5, 60, 4, 576, 16, CFG1_CTF, 6, 2, model_sigma=6.0,
                     model_rmax=14.0, particle_format="mrc"),
     "toy64": Case("toy64", 64, 1.5, 200, 5, 576, 32, synth.PRODUCTION_GRID, 10, 1,

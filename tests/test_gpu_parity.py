@@ -144,7 +144,7 @@ def _compare_with_oracle(P, hi, pm, res, n):
     return near
 
 
-@pytest.mark.parametrize("name", ["toy32", "toy32psf", "toy36g2", "toy64", "cfg1", "cfg2_slice", "cfg4_slice"])
+@pytest.mark.parametrize("name", ["toy32", "toy32psf", "toy32d0", "toy32full", "toy36g2", "toy64", "cfg1", "cfg2_slice", "cfg4_slice"])
 def test_full_run_matches_oracle(setups, name):
     cd, hi, parts, eng, P = setups(name)
     eng.reset()
@@ -155,7 +155,7 @@ def test_full_run_matches_oracle(setups, name):
     assert len(near) <= max(1, P.M // 3), near
 
 
-@pytest.mark.parametrize("name", ["toy32", "toy32psf", "toy64", "cfg1", "cfg2_slice"])
+@pytest.mark.parametrize("name", ["toy32", "toy32psf", "toy32d0", "toy32full", "toy64", "cfg1", "cfg2_slice"])
 def test_full_run_matches_reference_golden(setups, name, golden_dir):
     cd, hi, parts, eng, P = setups(name)
     ref = parse_output_probabilities(os.path.join(golden_dir, name, "Output_Probabilities"))
