@@ -275,3 +275,30 @@ def test_mrc_ingest_on_device_matches_host_reader(setups):
     b, _ = e2.download()
     e2.close()
     assert a.tobytes() == b.tobytes()
+
+
+@pytest.mark.parametrize("n", [32, 36, 48, 64, 96, 128, 160, 192, 224, 256, 288, 320, 360, 384, 400])
+def test_every_instantiated_image_edge_matches_oracle(n):
+    """One tiny run per image edge the kernels are instantiated for (mixed radices 2/3/5/7,
+    one or two CTAs per SM, 8-12 warps): log P and arg-max against the oracle."""
+    _need_gpu()
+    from bioem_b200.cases import CFG1_CTF, Case
+    case = Case(f"edge{n}", n, 1.5, 40, 2, 576, 2, CFG1_CTF, min(10, n // 4), 1,
+                model_sigma=n / 12.0, model_rmax=n / 4.0, particle_format="mrc")
+    cd = build_case(case)
+    hi, parts = api.inputs_for_case(cd)
+    eng = api.Engine(hi.cfg)
+    eng.upload_all(hi, parts)
+    eng.run()
+    pm, _ = eng.download()
+    eng.close()
+    P = pyoracle.Prepared(cd.case, cd.model, cd.quats, cd.particles)
+    ref = P.run()["prob"]
+    for m in range(P.M):
+        lg = hi.final_logprob(pm[m]["Total"], pm[m]["Constoadd"])
+        lo = P.final_logprob(ref[m]["Total"], ref[m]["Constoadd"])
+        assert abs(lg - lo) <= 1e-5 * abs(lo) + 1e-3, (n, m, lg, lo)
+        same = all(pm[m][k] == ref[m][k] for k in ("orient", "conv", "cent_x", "cent_y"))
+        if not same:
+            lp_at = P.logpro_at(m, int(pm[m]["orient"]), int(pm[m]["conv"]), int(pm[m]["cent_x"]), int(pm[m]["cent_y"]))
+            assert ref[m]["Constoadd"] - lp_at <= 1e-5 * abs(lo) + 1e-3, ("not a near-tie", n, m)
