@@ -679,7 +679,7 @@ template <int N> __host__ __device__ constexpr int lik_window_groups(int maxD)
   using L = Lay<N>;
   constexpr int HALF = L::R2 / 2;
   const int need = maxD / L::R1 + 1;
-  return (need <= 4 && need < HALF) ? need : HALF;
+  return (need <= 7 && need < HALF) ? need : HALF;
 }
 
 // Shared-memory plan of the fused kernel (W = window groups, NK = kept radix-R2 outputs).

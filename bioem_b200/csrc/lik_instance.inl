@@ -37,5 +37,14 @@ extern "C" cudaError_t BIOEM_CAT(bioem_lik_launch_, BIOEM_N)(const bioem::LikPar
   if constexpr (HALF > 4)
     if (w == 4)
       return bioem::lik_launch_w<4>(*p, nblocks, s);
+  if constexpr (HALF > 5)
+    if (w == 5)
+      return bioem::lik_launch_w<5>(*p, nblocks, s);
+  if constexpr (HALF > 6)
+    if (w == 6)
+      return bioem::lik_launch_w<6>(*p, nblocks, s);
+  if constexpr (HALF > 7)
+    if (w == 7)
+      return bioem::lik_launch_w<7>(*p, nblocks, s);
   return bioem::lik_launch_w<HALF>(*p, nblocks, s);
 }
