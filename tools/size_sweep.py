@@ -15,8 +15,8 @@ ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 bw = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
     os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
 sizes = [int(a) for a in sys.argv[1:]] or [32, 36, 48, 64, 96, 128, 160, 192, 224, 256, 288, 320, 360, 384, 400]
-print("| N | R1 x R2 | window | likelihoods | ns / likelihood | M likelihoods/s | HBM roofline ns | frac |")
-print("|---|---|---|---|---|---|---|---|")
+print("| N | window | likelihoods | ns / likelihood | M likelihoods/s | HBM roofline ns | frac |")
+print("|---|---|---|---|---|---|---|")
 for n in sizes:
     maxd = min(40, n // 4)
     case = Case(f"sweep{n}", n, 1.0 if n >= 200 else 1.5, 200, 64, 576, 16, synth.PRODUCTION_GRID, maxd, 1,
@@ -27,7 +27,7 @@ for n in sizes:
     try:
         eng = api.Engine(hi.cfg)
     except api.BioemError as e:
-        print(f"| {n} | - | {2 * maxd + 1}² | - | {str(e)[:60]} | | | |")
+        print(f"| {n} | {2 * maxd + 1}² | - | {str(e)[:60]} | | | |")
         continue
     eng.upload_all(hi, parts)
     eng.run()
@@ -39,4 +39,4 @@ for n in sizes:
     ns = 1e6 * ms / lik
     roof = 8.0 * n * (n // 2 + 1) / bw
     eng.close()
-    print(f"| {n} | | {2 * maxd + 1}² | {lik} | {ns:.1f} | {1e3 / ns:.2f} | {roof:.1f} | {roof / ns:.2f} |", flush=True)
+    print(f"| {n} | {2 * maxd + 1}² | {lik} | {ns:.1f} | {1e3 / ns:.2f} | {roof:.1f} | {roof / ns:.2f} |", flush=True)
