@@ -698,8 +698,12 @@ template <int N> struct LikGeo
   // Exchange tile E[k1][c][n2] (float2): pass 1 stores with lane = c*R2 + n2 at k1*ES + c*CS + n2
   // (contiguous per half warp), pass 2 loads with lane = k1*KC + c at the same address for
   // n2 = 0..R2-1: conflict-free when c*CS == c and k1*ES == k1*KC (mod 16 bank pairs).
-  static constexpr int CS = ((L::R2 - 1 + 15) / 16) * 16 + 1;
-  static constexpr int ES = KC * CS + ((KC - KC * CS) % 16 + 16) % 16;
+  // With two columns of sixteen sub-sequences per warp (N = 128 .. 320) pass 2 loads pairs of
+  // values as 128-bit words: c*CS and k1*ES are then multiples of two float2 whose halves run
+  // through all eight 16-byte bank groups of a quarter warp (CS = 18, ES = 36).
+  static constexpr bool WIDE = (KC == 2 && L::R2 == 16);
+  static constexpr int CS = WIDE ? 18 : ((L::R2 - 1 + 15) / 16) * 16 + 1;
+  static constexpr int ES = WIDE ? 36 : KC * CS + ((KC - KC * CS) % 16 + 16) % 16;
   static constexpr int YS0 = L::NCOL + ((KC - L::NCOL) % 16 + 16) % 16;
   static constexpr int YS = YS0 > L::NCOL ? YS0 : YS0 + 16; // index NCOL of a row must exist
   static constexpr int EW = L::R1 * ES;                     // float2 per warp
@@ -713,7 +717,7 @@ template <int N> __host__ __device__ constexpr int lik_window_groups(int maxD);
 
 // likelihoods whose double-precision bookkeeping is deferred, then done by up to 32 lanes at once
 // (16 where a single CTA already needs nearly all of the shared memory)
-template <int N> __host__ __device__ constexpr int lik_pending() { return N > 224 ? 16 : 32; }
+template <int N> __host__ __device__ constexpr int lik_pending() { return 16; }
 
 // warps per CTA of the fused kernel.  Up to N = 224 two CTAs of 8 warps share an SM.  Measured
 // on B200 at N = 224 (tools/build_variant.py): 8 warps 55.1 ns/likelihood, 7 warps (which would
@@ -745,6 +749,7 @@ template <int N> struct LikSmem
   // of 4 warps, so 7 warps cost as many as 8), one CTA per SM above
   static constexpr int MAXREG = N <= 224 ? 128 : (65536 / (32 * ((NWARP + 3) / 4 * 4))) / 8 * 8 > 255 ? 255 : (65536 / (32 * ((NWARP + 3) / 4 * 4))) / 8 * 8;
   static constexpr int KC = G::KC, CS = G::CS, ES = G::ES, YS = G::YS, EW = G::EW;
+  static constexpr bool WIDE = G::WIDE;
   __host__ __device__ static constexpr int nk(int W) { return G::nk(W); }
   __host__ __device__ static constexpr size_t bytes(int W) { return G::dyn_bytes(W, NWARP); }
 };
@@ -1078,9 +1083,22 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
       {
         const int k1 = item / KC, cc = item % KC;
         float2 y[R2];
+        if constexpr (SM::WIDE)
+        {
 #pragma unroll
-        for (int n2 = 0; n2 < R2; n2++)
-          y[n2] = E[k1 * ES + cc * CS + n2];
+          for (int n2 = 0; n2 < R2; n2 += 2)
+          {
+            const float4 w = *reinterpret_cast<const float4 *>(&E[k1 * ES + cc * CS + n2]);
+            y[n2] = make_float2(w.x, w.y);
+            y[n2 + 1] = make_float2(w.z, w.w);
+          }
+        }
+        else
+        {
+#pragma unroll
+          for (int n2 = 0; n2 < R2; n2++)
+            y[n2] = E[k1 * ES + cc * CS + n2];
+        }
         bfft::Dft<R2, 1>::run(y);
         float2 *Ycol = Y + k1 * YS + ch * KC + cc;
         bfft::static_for<0, NK>([&](auto j_) {
@@ -1180,9 +1198,22 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
           if (item < KC * R1 && cc < npl)
           {
             float2 y[R2];
+            if constexpr (SM::WIDE)
+            {
 #pragma unroll
-            for (int n2 = 0; n2 < R2; n2++)
-              y[n2] = E[k1 * ES + cc * CS + n2];
+              for (int n2 = 0; n2 < R2; n2 += 2)
+              {
+                const float4 w = *reinterpret_cast<const float4 *>(&E[k1 * ES + cc * CS + n2]);
+                y[n2] = make_float2(w.x, w.y);
+                y[n2 + 1] = make_float2(w.z, w.w);
+              }
+            }
+            else
+            {
+#pragma unroll
+              for (int n2 = 0; n2 < R2; n2++)
+                y[n2] = E[k1 * ES + cc * CS + n2];
+            }
             bfft::Dft<R2, 1>::run(y);
             const int wa = 2 * (p0 + cc);
             const bool vb = wa + 1 < nw;
