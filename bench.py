@@ -271,6 +271,7 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.workload, budget_s=args.cpu_seconds)
+            line["reference_gpu"] = reference_gpu(args.workload)
         print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:
@@ -319,6 +320,38 @@ def cpu_baseline(workload: str, budget_s: float = 15.0) -> dict:
             "sample": f"unmodified reference (FFTW-API shim FFT, Algo 1, OpenMP {threads} threads) on the first "
                       f"{n_or} orientations x all CTFs x {n_part} particles of {workload} = {n} likelihoods in {s:.2f} s "
                       f"(reference's own run() timer)"}
+
+
+def reference_gpu(workload: str, n_orient: int = 8) -> dict:
+    """The reference's own CUDA path (bioem_cuda.cu + cuFFT rebuilt for sm_100a, oracle/_ref/bioEM_ref_cuda,
+    GPU=1 GPUWORKLOAD=100) on the first n_orient orientations of the workload on this box's GPU 0:
+    likelihoods/s from its own per-orientation timer ("reference GPU on the same box").
+    Reported beside the CPU baseline; never part of a timed region of ours."""
+    refbin = os.path.join(ROOT, "oracle", "_ref", "bioEM_ref_cuda")
+    if not os.path.exists(refbin):
+        return {"value": None, "unit": "likelihoods/s", "sample": "oracle/_ref/bioEM_ref_cuda not present"}
+    from bioem_b200.cases import build_case, reference_cli
+    cname, m_full, _ = WORKLOADS[workload]
+    try:
+        with tempfile.TemporaryDirectory() as d:
+            cd = build_case(cname, d, n_particles=m_full, n_orient=n_orient)
+            env = {**os.environ, "GPU": "1", "GPUWORKLOAD": "100", "GPUDEVICE": "0", "BIOEM_DEBUG_OUTPUT": "1",
+                   "OMP_NUM_THREADS": str(os.cpu_count() or 1)}
+            r = subprocess.run([refbin] + reference_cli(cd), cwd=d, env=env, capture_output=True, text=True,
+                               timeout=300)
+        if r.returncode != 0:
+            raise RuntimeError((r.stdout[-300:] + r.stderr[-300:]).replace("\n", " | "))
+        mean = None
+        for ln in r.stdout.splitlines():
+            if "Total time of projection" in ln:
+                mean = float(ln.split("Mean")[1].split("sec")[0])
+        per_or = cd.case.n_ctf * cd.case.n_particles
+        return {"value": round(per_or / mean, 1), "unit": "likelihoods/s",
+                "sample": f"unmodified reference CUDA path (bioem_cuda.cu + cuFFT, nvcc sm_100a, GPU=1 GPUWORKLOAD=100) "
+                          f"on 1 GPU: mean {mean * 1e3:.1f} ms per orientation over the first {n_orient} orientations x "
+                          f"{cd.case.n_ctf} CTFs x {cd.case.n_particles} particles of {workload} (its own timer)"}
+    except Exception as e:  # a reported side number: never fail the bench for it
+        return {"value": None, "unit": "likelihoods/s", "sample": f"failed: {e}"[:300]}
 
 
 def run_reference(args):

@@ -108,3 +108,31 @@ def test_binary_multi_gpu_split_equals_single(tmp_path):
         np.testing.assert_allclose(a["logp"], b["logp"], atol=2e-4)
         for k in ("cent_x", "cent_y", "angles", "env", "defocus"):
             np.testing.assert_array_equal(a[k], b[k])
+
+
+REF_CUDA = os.path.join(ROOT, "oracle", "_ref", "bioEM_ref_cuda")
+
+
+@pytest.mark.parametrize("name", ["toy64", "cfg2_slice"])
+def test_binary_agrees_with_reference_cuda_path_on_this_gpu(name, tmp_path):
+    """The reference's own CUDA path (bioem_cuda.cu + cuFFT, rebuilt for sm_100a by oracle/Makefile) run on
+    the same box and the same files: same maximizing orientation / CTF / displacement, log P within 1e-4
+    relative.  The checker is executed, never linked: skipped when it was not built."""
+    if not os.path.exists(REF_CUDA):
+        pytest.skip("oracle/_ref/bioEM_ref_cuda not built")
+    cd = _run(name, tmp_path)
+    os.rename(tmp_path / "Output_Probabilities", tmp_path / "ours")
+    r = subprocess.run([REF_CUDA] + reference_cli(cd), cwd=tmp_path, capture_output=True, text=True, timeout=600,
+                       env={**os.environ, "GPU": "1", "GPUWORKLOAD": "100", "GPUDEVICE": "0"})
+    if r.returncode != 0:
+        pytest.skip("reference CUDA build does not run on this box: " + (r.stdout + r.stderr)[-300:])
+    got, ref = parse_output_probabilities(str(tmp_path / "ours")), parse_output_probabilities(
+        str(tmp_path / "Output_Probabilities"))
+    same = 0
+    for m in range(len(ref["logp"])):
+        assert abs(got["logp"][m] - ref["logp"][m]) <= 1e-4 * abs(ref["logp"][m])
+        same += (got["cent_x"][m] == ref["cent_x"][m] and got["cent_y"][m] == ref["cent_y"][m]
+                 and np.allclose(got["angles"][m], ref["angles"][m], atol=1.1e-4)
+                 and abs(got["defocus"][m] - ref["defocus"][m]) < 1.1e-4 and abs(got["env"][m] - ref["env"][m]) < 1.1e-4)
+    # cuFFT + --use_fast_math round differently from FFTW: a near-tie may flip for one image
+    assert same >= len(ref["logp"]) - max(1, len(ref["logp"]) // 3)
