@@ -171,7 +171,11 @@ static cudaError_t launch_conv(const float4 *proj, const float4 *ctf, const doub
   ctf_conv_kernel<N><<<g, NT, 0, s>>>(proj, ctf, prior, conv, cpar, C, Nt);
   return cudaGetLastError();
 }
-template <int N> static size_t lik_smem(int maxD) { return lik_smem_bytes<N>(maxD); }
+// dynamic + (an upper bound of the) static shared memory of the fused kernel
+template <int N> static size_t lik_smem(int maxD, int nwp)
+{
+  return lik_smem_bytes<N>(maxD, nwp) + (size_t) lik_pending<N>() * LikSmem<N>::NWARP * 24 + 256;
+}
 
 static cudaError_t do_pack(int N, const float2 *src, float4 *dst, int nmaps, cudaStream_t s)
 {
@@ -239,13 +243,13 @@ static cudaError_t do_lik(int N, const LikParams &p, int nblocks, int maxD, cuda
   }
   return cudaErrorInvalidValue;
 }
-static size_t smem_for(int N, int maxD)
+static size_t smem_for(int N, int maxD, int nwp)
 {
   switch (N)
   {
 #define X(n)                                                                                              \
   case n:                                                                                                 \
-    return lik_smem<n>(maxD);
+    return lik_smem<n>(maxD, nwp);
     BIOEM_SIZES(X)
 #undef X
   }
@@ -329,7 +333,7 @@ int bioem_b200_create(const bioem_b200_config *cfg, int device, bioem_b200_handl
   CU(cudaSetDevice(device));
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, device));
-  if (smem_for(N, cfg->maxDisplaceCenter) > (size_t) prop.sharedMemPerBlockOptin)
+  if (smem_for(N, cfg->maxDisplaceCenter, nw + (nw & 1)) > (size_t) prop.sharedMemPerBlockOptin)
     return fail(BIOEM_B200_ERR_INVALID, "displacement window does not fit in shared memory for this image size");
   bioem_b200_context *h = new bioem_b200_context;
   h->cfg = *cfg;

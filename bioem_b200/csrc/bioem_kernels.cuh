@@ -708,9 +708,14 @@ template <int N> struct LikGeo
   static constexpr int YS = YS0 > L::NCOL ? YS0 : YS0 + 16; // index NCOL of a row must exist
   static constexpr int EW = L::R1 * ES;                     // float2 per warp
   __host__ __device__ static constexpr int nk(int W) { return 2 * W >= L::R2 ? L::R2 : 2 * W; }
-  __host__ __device__ static constexpr size_t dyn_bytes(int W, int nwarp)
+  // Above N = 224 one CTA fills an SM and the warp count is what the shared memory leaves: Y then
+  // holds exactly the window rows (slot = window row index, nwp of them) instead of whole radix
+  // output groups, which buys two more warps at N = 320 / 360 and the 24 x 16 split at N = 384.
+  static constexpr bool COMPACT = N > 224;
+  __host__ __device__ static constexpr int rows(int W, int nwp) { return COMPACT ? nwp : nk(W) * L::R1; }
+  __host__ __device__ static constexpr size_t dyn_bytes(int W, int nwarp, int nwp)
   {
-    return ((size_t) nk(W) * L::R1 * YS + (size_t) nwarp * EW) * sizeof(float2) + ((N + 15) & ~15) + 256;
+    return ((size_t) rows(W, nwp) * YS + (size_t) nwarp * EW) * sizeof(float2) + ((N + 15) & ~15) + 256;
   }
 };
 template <int N> __host__ __device__ constexpr int lik_window_groups(int maxD);
@@ -734,7 +739,7 @@ template <int N> __host__ __device__ constexpr int lik_warps()
     return 8;
   constexpr size_t budget = 227 * 1024 - 1024;
   for (int nw = 12; nw > 8; nw -= 2)
-    if (LikGeo<N>::dyn_bytes(lik_window_groups<N>(40), nw) + (size_t) lik_pending<N>() * nw * 24 + 256 <= budget)
+    if (LikGeo<N>::dyn_bytes(lik_window_groups<N>(40), nw, 82) + (size_t) lik_pending<N>() * nw * 24 + 256 <= budget)
       return nw;
   return 8;
 #endif
@@ -751,11 +756,11 @@ template <int N> struct LikSmem
   static constexpr int KC = G::KC, CS = G::CS, ES = G::ES, YS = G::YS, EW = G::EW;
   static constexpr bool WIDE = G::WIDE;
   __host__ __device__ static constexpr int nk(int W) { return G::nk(W); }
-  __host__ __device__ static constexpr size_t bytes(int W) { return G::dyn_bytes(W, NWARP); }
+  __host__ __device__ static constexpr size_t bytes(int W, int nwp) { return G::dyn_bytes(W, NWARP, nwp); }
 };
-template <int N> __host__ __device__ constexpr size_t lik_smem_bytes(int maxD)
+template <int N> __host__ __device__ constexpr size_t lik_smem_bytes(int maxD, int nwp)
 {
-  return LikSmem<N>::bytes(lik_window_groups<N>(maxD));
+  return LikSmem<N>::bytes(lik_window_groups<N>(maxD), nwp);
 }
 
 // 2^x, one MUFU.EX2 (results below the normal range flush to zero)
@@ -825,14 +830,14 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
   constexpr int NK = SM::nk(W); // radix-R2 output groups kept
   constexpr int R1 = L::R1, R2 = L::R2, KC = L::KC, NCH = L::NCH;
   constexpr int ES = SM::ES, CS = SM::CS, YS = SM::YS, NWARP = SM::NWARP;
-  constexpr int NROWS = NK * R1;          // row slots of Y
+  constexpr bool COMPACT = SM::G::COMPACT;
   constexpr int P2 = (KC * R1 + 31) / 32; // pass-2 trips
   constexpr int NPEND = lik_pending<N>();
   auto k2_of = [](int j) { return (NK == R2) ? j : (j < W ? j : R2 - NK + j); };
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2 *Y = reinterpret_cast<float2 *>(smem_raw); // [NROWS][YS]
-  float2 *Eall = Y + (size_t) NROWS * YS;
+  float2 *Eall = Y + (size_t) SM::G::rows(W, p.nwp) * YS;
   unsigned char *WT = reinterpret_cast<unsigned char *>(Eall + (size_t) NWARP * SM::EW);
   unsigned char *RS = WT + ((N + 15) & ~15);
   // ring of likelihoods waiting for their bookkeeping, one entry per warp and likelihood:
@@ -862,9 +867,10 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
     {
       const int k2 = i / R1, k1 = i % R1;
       const int j = (NK == R2) ? k2 : (k2 < W ? k2 : k2 - (R2 - NK));
-      RS[w] = (unsigned char) (j * R1 + k1);
+      const int rs = COMPACT ? (int) w : j * R1 + k1;
+      RS[w] = (unsigned char) rs;
       if ((int) w == nw - 1)
-        RS[nw] = (unsigned char) (j * R1 + k1); // padding row of an odd window: any valid slot
+        RS[nw] = (unsigned char) rs; // padding row of an odd window: any valid slot
     }
   }
   const unsigned mbar_addr = (unsigned) __cvta_generic_to_shared(&s_mbar);
@@ -903,6 +909,25 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
     });
   }
   static_assert(P2 * NK <= 32, "validity mask must fit one register");
+  // compact row slots: byte j of cslot[t] = slot of output j of this lane's pass-2 item t in the
+  // column pass (255: not a window row, not stored)
+  constexpr int CSW = COMPACT ? (NK + 3) / 4 : 1;
+  unsigned cslot[P2][CSW];
+  if constexpr (COMPACT)
+  {
+#pragma unroll
+    for (int t = 0; t < P2; t++)
+    {
+      const int k1 = ((lane + 32 * t) / KC) % R1;
+#pragma unroll
+      for (int q = 0; q < CSW; q++)
+        cslot[t][q] = 0;
+      bfft::static_for<0, NK>([&](auto j_) {
+        constexpr int j = decltype(j_)::value;
+        cslot[t][j / 4] |= (unsigned) WT[k1 + R1 * k2_of(j)] << (8 * (j % 4));
+      });
+    }
+  }
   // exp(a*log1p(t)) = 2^(t*(c1 + t*(c2 + t*c3))), a = (3 - Nt)/2, for the tiny t >= 0 that matter;
   // decreasing in t and 0 for huge t
   const float c1 = p.ex2coef, c2 = -0.5f * p.ex2coef, c3 = p.ex2coef * (1.f / 3.f);
@@ -1100,11 +1125,24 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
             y[n2] = E[k1 * ES + cc * CS + n2];
         }
         bfft::Dft<R2, 1>::run(y);
-        float2 *Ycol = Y + k1 * YS + ch * KC + cc;
-        bfft::static_for<0, NK>([&](auto j_) {
-          constexpr int j = decltype(j_)::value;
-          Ycol[j * R1 * YS] = y[k2_of(j)];
-        });
+        if constexpr (COMPACT)
+        {
+          float2 *Ycol = Y + ch * KC + cc;
+          bfft::static_for<0, NK>([&](auto j_) {
+            constexpr int j = decltype(j_)::value;
+            const unsigned sl = (cslot[t][j / 4] >> (8 * (j % 4))) & 255u;
+            if (sl != 255u)
+              Ycol[sl * YS] = y[k2_of(j)];
+          });
+        }
+        else
+        {
+          float2 *Ycol = Y + k1 * YS + ch * KC + cc;
+          bfft::static_for<0, NK>([&](auto j_) {
+            constexpr int j = decltype(j_)::value;
+            Ycol[j * R1 * YS] = y[k2_of(j)];
+          });
+        }
       }
     }
     __syncwarp();

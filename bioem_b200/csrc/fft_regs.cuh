@@ -323,7 +323,7 @@ BFFT_GEO(256, 16, 16, 16, 16)
 BFFT_GEO(288, 18, 16, 16, 12)
 BFFT_GEO(320, 20, 16, 16, 12)
 BFFT_GEO(360, 24, 15, 20, 10)
-BFFT_GEO(384, 16, 24, 16, 10)
+BFFT_GEO(384, 24, 16, 16, 10)
 BFFT_GEO(400, 16, 25, 20, 10)
 #undef BFFT_GEO
 

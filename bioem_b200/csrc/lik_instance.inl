@@ -7,7 +7,7 @@ namespace bioem
 {
 template <int W> static cudaError_t lik_launch_w(const LikParams &p, int nblocks, cudaStream_t s)
 {
-  const size_t smem = LikSmem<BIOEM_N>::bytes(W);
+  const size_t smem = LikSmem<BIOEM_N>::bytes(W, p.nwp);
   // attribute is per device context: set on every launch (cheap next to the kernel)
   cudaError_t e = cudaFuncSetAttribute(likelihood_kernel<BIOEM_N, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
   if (e != cudaSuccess)
