@@ -37,6 +37,7 @@ PROB_MAP_DTYPE = np.dtype([("Total", "<f8"), ("Constoadd", "<f8"), ("cent_x", "<
                            ("cent_y", "<i4"), ("orient", "<i4"), ("conv", "<i4"),
                            ("norm", "<f4"), ("mu", "<f4")])
 PROB_ANGLE_DTYPE = np.dtype([("forAngles", "<f8"), ("ConstAngle", "<f8")])
+TOP_ANGLE_DTYPE = np.dtype([("orient", "<i4"), ("pad", "<i4"), ("forAngles", "<f8"), ("ConstAngle", "<f8")])
 MODEL_POINT_DTYPE = np.dtype([("pos", "<f4", 3), ("quat4", "<f4"), ("radius", "<f4"),
                               ("density", "<f4")])
 assert PROB_MAP_DTYPE.itemsize == 40 and PROB_ANGLE_DTYPE.itemsize == 16
@@ -49,7 +50,7 @@ EXPORTS = [
     "bioem_b200_upload_ctf_real", "bioem_b200_upload_particles", "bioem_b200_upload_particles_mrc",
     "bioem_b200_upload_particles_fft",
     "bioem_b200_reset",
-    "bioem_b200_run", "bioem_b200_synchronize", "bioem_b200_download",
+    "bioem_b200_run", "bioem_b200_synchronize", "bioem_b200_download", "bioem_b200_download_top_angles",
     "bioem_b200_partial_bytes", "bioem_b200_export_partial", "bioem_b200_import_partials",
     "bioem_b200_merge_host", "bioem_b200_stream", "bioem_b200_device_angles", "bioem_b200_stats",
     "bioem_b200_kernel_time", "bioem_b200_debug_projection", "bioem_b200_debug_convolved",
@@ -95,6 +96,7 @@ def lib():
     L.bioem_b200_run.argtypes = [vp, C.c_int, C.c_int]
     L.bioem_b200_synchronize.argtypes = [vp]
     L.bioem_b200_download.argtypes = [vp, vp, vp]
+    L.bioem_b200_download_top_angles.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp]
     L.bioem_b200_partial_bytes.argtypes = [vp]
     L.bioem_b200_partial_bytes.restype = C.c_size_t
     L.bioem_b200_export_partial.argtypes = [vp, vp]
@@ -312,6 +314,14 @@ class Engine:
         _chk(lib().bioem_b200_download(self._h, pm.ctypes.data, pa.ctypes.data if pa is not None else None),
              "download")
         return pm, pa
+
+    def download_top_angles(self, k: int, o_begin: int = 0, o_end: int | None = None) -> np.ndarray:
+        """[M, k] rows (orient, forAngles, ConstAngle): the k most probable orientations of every
+        particle among [o_begin, o_end), most probable first (reference bioem.cpp:1254-1290)."""
+        out = np.zeros((self.M, k), dtype=TOP_ANGLE_DTYPE)
+        _chk(lib().bioem_b200_download_top_angles(self._h, int(o_begin), int(self.O if o_end is None else o_end),
+                                                  int(k), out.ctypes.data), "download_top_angles")
+        return out
 
     # ---- multi-GPU plumbing
     def partial_bytes(self) -> int:

@@ -846,6 +846,31 @@ int bioem_b200_download(bioem_b200_handle h, bioem_b200_prob_map *maps_out, bioe
   return BIOEM_B200_OK;
 }
 
+int bioem_b200_download_top_angles(bioem_b200_handle h, int oBegin, int oEnd, int K, bioem_b200_top_angle *out)
+{
+  if (!h || !out || K <= 0 || oBegin < 0 || oEnd > (h ? h->O : 0) || oBegin > oEnd)
+    return fail(BIOEM_B200_ERR_INVALID, "download_top_angles: bad argument");
+  if (!h->cfg.writeAngles || !h->d_angtab)
+    return fail(BIOEM_B200_ERR_STATE, "download_top_angles: the handle was created with writeAngles == 0");
+  if (!h->state_ready)
+    return fail(BIOEM_B200_ERR_STATE, "download_top_angles: nothing has been run");
+  static_assert(sizeof(TopAngleOut) == sizeof(bioem_b200_top_angle) && sizeof(TopAngleOut) == 24, "result layout");
+  CU(cudaSetDevice(h->device));
+  const size_t n = (size_t) h->M * K;
+  double *d_key = nullptr;
+  TopAngleOut *d_top = nullptr;
+  CU(cudaMallocAsync((void **) &d_key, n * sizeof(double), h->stream));
+  CU(cudaMallocAsync((void **) &d_top, n * sizeof(TopAngleOut), h->stream));
+  top_angles_kernel<<<(h->M + 63) / 64, 64, 0, h->stream>>>(h->d_angtab, h->M, oBegin, oEnd, K, d_key, d_top);
+  CU(cudaGetLastError());
+  h->launches++;
+  CU(cudaMemcpyAsync(out, d_top, n * sizeof(TopAngleOut), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaFreeAsync(d_key, h->stream));
+  CU(cudaFreeAsync(d_top, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return BIOEM_B200_OK;
+}
+
 size_t bioem_b200_partial_bytes(bioem_b200_handle h) { return h ? sizeof(Running) * (size_t) h->M : 0; }
 
 int bioem_b200_export_partial(bioem_b200_handle h, void *device_dst)

@@ -1469,6 +1469,59 @@ __global__ void init_angles_kernel(ProbAngleOut *a, size_t n)
   a[i].ConstAngle = kMinProb;
 }
 
+// WRITE_PROB_ANGLES: the K most probable orientations of every particle among the orientations
+// [oBegin, oEnd) of the angle table, selected where the table lies (reference: a size-K min-heap of
+// (log(forAngles) + ConstAngle, orientation) per particle on the host, bioem.cpp:1254-1290).  One
+// thread per particle: consecutive threads read consecutive 16-byte rows of one orientation.
+// The list top[m][0..K) is kept sorted in descending (logp, orientation) order, i.e. the order in
+// which the reference's heap is finally emptied; a full list only takes a strictly greater logp,
+// like the heap (first come stays on equal values).
+struct TopAngleOut // == bioem_b200_top_angle
+{
+  int orient, pad;
+  double forAngles, ConstAngle;
+};
+__global__ void top_angles_kernel(const ProbAngleOut *__restrict__ tab, int M, int oBegin, int oEnd, int K,
+                                  double *__restrict__ key, TopAngleOut *__restrict__ top)
+{
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M)
+    return;
+  double *kk = key + (size_t) m * K;
+  TopAngleOut *tt = top + (size_t) m * K;
+  int n = 0;
+  for (int o = oBegin; o < oEnd; o++)
+  {
+    const ProbAngleOut r = tab[(size_t) o * M + m];
+    const double lp = log(r.forAngles) + r.ConstAngle;
+    if (n == K && !(kk[K - 1] < lp))
+      continue;
+    // position in descending (logp, orientation) order; o is the largest orientation so far, so
+    // the new row goes in front of equal keys
+    int pos = (n < K) ? n : K - 1;
+    while (pos > 0 && !(kk[pos - 1] > lp))
+    {
+      kk[pos] = kk[pos - 1];
+      tt[pos] = tt[pos - 1];
+      pos--;
+    }
+    kk[pos] = lp;
+    tt[pos].orient = o;
+    tt[pos].pad = 0;
+    tt[pos].forAngles = r.forAngles;
+    tt[pos].ConstAngle = r.ConstAngle;
+    if (n < K)
+      n++;
+  }
+  for (int i = n; i < K; i++)
+  {
+    tt[i].orient = -1;
+    tt[i].pad = 0;
+    tt[i].forAngles = 0.0;
+    tt[i].ConstAngle = kMinProb;
+  }
+}
+
 // Running -> bioem_Probability_map (norm / mu as bioem_algorithm.h:106-111)
 __global__ void finalize_kernel(const Running *__restrict__ state, const float *__restrict__ sumRef, int M, int nw,
                                 int npos, int maxD, int Gs, float Ntotpi, ProbMapOut *__restrict__ out)

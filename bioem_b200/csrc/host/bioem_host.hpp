@@ -61,7 +61,10 @@ void read_model(const Options &o, const Params &p, std::vector<bioem_b200_model_
 void read_particles(const Options &o, const Params &p, std::vector<float> &maps, int &nMaps, bool &rawMRC);
 // what the reference's MRC reader does to a raw stack, on the host (for --DumpMaps and the test hook)
 void mrc_host_ingest(const Params &p, std::vector<float> &maps, int nMaps);
+// cand: WRITE_PROB_ANGLES candidates, nMaps x nCand rows in ascending orientation order (orient -1 = unused): the
+// per-GPU lists of most probable orientations selected on the device (bioem_b200_download_top_angles)
 void write_outputs(const Options &o, const Params &p, const bioem_b200_config &cfg,
-                   const std::vector<bioem_b200_prob_map> &pm, const std::vector<bioem_b200_prob_angle> &pa, int nMaps);
+                   const std::vector<bioem_b200_prob_map> &pm, const std::vector<bioem_b200_top_angle> &cand, int nCand,
+                   int nMaps);
 
 } // namespace bhost

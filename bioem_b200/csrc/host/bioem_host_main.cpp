@@ -35,7 +35,8 @@ namespace bhost
 
 // reference bioem.cpp:1046-1374 (ofstream, fixed, precision OUTPUT_PRECISION = 4, defs.h:177)
 void write_outputs(const Options &o, const Params &p, const bioem_b200_config &cfg,
-                   const std::vector<bioem_b200_prob_map> &pm, const std::vector<bioem_b200_prob_angle> &pa, int nMaps)
+                   const std::vector<bioem_b200_prob_map> &pm, const std::vector<bioem_b200_top_angle> &cand, int nCand,
+                   int nMaps)
 {
   const char *stars = "************************* HEADER:: NOTATION *******************************************\n";
   const double addc = 0.5 * log(M_PI) + (1 - cfg.Ntotpi * 0.5) * (log(2 * M_PI) + 1) + log(cfg.volu);
@@ -79,7 +80,6 @@ void write_outputs(const Options &o, const Params &p, const bioem_b200_config &c
     out << "**** Remark: Using Prior Proability in Angles ****\n";
   out << stars << "\n";
 
-  const int O = p.nOrient();
   for (int m = 0; m < nMaps; m++)
   {
     const bioem_b200_prob_map &r = pm[m];
@@ -118,20 +118,23 @@ void write_outputs(const Options &o, const Params &p, const bioem_b200_config &c
 
     if (cfg.writeAngles)
     {
-      // the K most probable orientations of this image, most probable first (min-heap of size K)
+      // the K most probable orientations of this image, most probable first: the reference's min-heap of
+      // size K (bioem.cpp:1254-1290), fed with the rows the GPUs kept, in ascending orientation order
       const unsigned K = (unsigned) cfg.writeAngles;
-      typedef std::pair<double, int> PI;
+      typedef std::pair<double, int> PI; // (logp, index into this image's candidate rows)
       std::priority_queue<PI, std::vector<PI>, std::greater<PI>> q;
-      for (int io = 0; io < O; io++)
+      const bioem_b200_top_angle *rows = &cand[(size_t) m * nCand];
+      for (int i = 0; i < nCand; i++)
       {
-        const bioem_b200_prob_angle &pr = pa[(size_t) io * nMaps + m];
-        const double logp = log(pr.forAngles) + pr.ConstAngle + addc;
+        if (rows[i].orient < 0)
+          continue;
+        const double logp = log(rows[i].forAngles) + rows[i].ConstAngle + addc;
         if (q.size() < K)
-          q.push(PI(logp, io));
+          q.push(PI(logp, i));
         else if (q.top().first < logp)
         {
           q.pop();
-          q.push(PI(logp, io));
+          q.push(PI(logp, i));
         }
       }
       std::vector<PI> best(q.size());
@@ -142,8 +145,8 @@ void write_outputs(const Options &o, const Params &p, const bioem_b200_config &c
       }
       for (const PI &b : best)
       {
-        const int io = b.second;
-        const bioem_b200_prob_angle &pr = pa[(size_t) io * nMaps + m];
+        const bioem_b200_top_angle &pr = rows[b.second];
+        const int io = pr.orient;
         double logp = b.first;
         if (p.yespriorAngles)
           logp += p.angprior[io];
@@ -262,9 +265,9 @@ int main(int argc, char **argv)
   const auto t1 = std::chrono::steady_clock::now();
 
   std::vector<std::vector<bioem_b200_prob_map>> parts(ndev, std::vector<bioem_b200_prob_map>(nMaps));
-  std::vector<bioem_b200_prob_angle> pa;
-  if (cfg.writeAngles)
-    pa.assign((size_t) O * nMaps, bioem_b200_prob_angle{0.0, -999999.});
+  // WRITE_PROB_ANGLES: every GPU keeps the K most probable orientations of its block per particle
+  const int K = cfg.writeAngles;
+  std::vector<std::vector<bioem_b200_top_angle>> tops(ndev);
   std::vector<std::string> errors(ndev);
   auto worker = [&](int g) {
     const int o0 = (int) ((long long) g * O / ndev), o1 = (int) ((long long) (g + 1) * O / ndev);
@@ -274,9 +277,8 @@ int main(int argc, char **argv)
         errors[g] = std::string(what) + ": " + bioem_b200_last_error();
       return rc == BIOEM_B200_OK;
     };
-    std::vector<bioem_b200_prob_angle> mine;
-    if (cfg.writeAngles)
-      mine.resize((size_t) O * nMaps);
+    if (K)
+      tops[g].resize((size_t) nMaps * K);
     bool ok = chk(bioem_b200_create(&cfg, g, &h), "create") &&
               chk(bioem_b200_upload_model(h, pts.data(), (int) pts.size(), NormDen), "upload_model") &&
               chk(bioem_b200_upload_orientations(h, par.angles.data(), O), "upload_orientations") &&
@@ -287,9 +289,9 @@ int main(int argc, char **argv)
                          : bioem_b200_upload_particles(h, maps.data(), nMaps),
                   "upload_particles") &&
               chk(bioem_b200_reset(h), "reset") && chk(bioem_b200_run(h, o0, o1), "run") &&
-              chk(bioem_b200_download(h, parts[g].data(), cfg.writeAngles ? mine.data() : nullptr), "download");
-    if (ok && cfg.writeAngles) // rows of this block only; blocks are disjoint
-      std::copy(mine.begin() + (size_t) o0 * nMaps, mine.begin() + (size_t) o1 * nMaps, pa.begin() + (size_t) o0 * nMaps);
+              chk(bioem_b200_download(h, parts[g].data(), nullptr), "download");
+    if (ok && K)
+      chk(bioem_b200_download_top_angles(h, o0, o1, K, tops[g].data()), "download_top_angles");
     if (h)
       bioem_b200_destroy(h);
   };
@@ -308,7 +310,19 @@ int main(int argc, char **argv)
   B200(bioem_b200_merge_host(flat.data(), ndev, nMaps, pm.data()));
   const auto t2 = std::chrono::steady_clock::now();
 
-  write_outputs(opt, par, cfg, pm, pa, nMaps);
+  // candidate rows per particle in ascending orientation order (blocks ascend with the GPU index)
+  const int nCand = K * ndev;
+  std::vector<bioem_b200_top_angle> cand((size_t) nMaps * nCand);
+  for (int m = 0; m < nMaps && K; m++)
+  {
+    bioem_b200_top_angle *row = &cand[(size_t) m * nCand];
+    for (int g = 0; g < ndev; g++)
+      std::copy(tops[g].begin() + (size_t) m * K, tops[g].begin() + (size_t) (m + 1) * K, row + (size_t) g * K);
+    std::stable_sort(row, row + nCand, [](const bioem_b200_top_angle &a, const bioem_b200_top_angle &b) {
+      return (unsigned) a.orient < (unsigned) b.orient; // -1 (unused) last
+    });
+  }
+  write_outputs(opt, par, cfg, pm, cand, nCand, nMaps);
   const auto t3 = std::chrono::steady_clock::now();
   auto sec = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
     return std::chrono::duration<double>(b - a).count();

@@ -69,6 +69,17 @@ typedef struct bioem_b200_prob_angle
   double ConstAngle;
 } bioem_b200_prob_angle;
 
+/* One row of the per-particle list of most probable orientations (WRITE_PROB_ANGLES):
+ * what the reference's heap of (log(forAngles) + ConstAngle, orientation) pairs keeps
+ * (bioem.cpp:1254-1290), 24 bytes.  orient = -1: fewer orientations than rows. */
+typedef struct bioem_b200_top_angle
+{
+  int orient;
+  int pad;
+  double forAngles;
+  double ConstAngle;
+} bioem_b200_top_angle;
+
 /* == bioem_model::bioem_model_point (reference include/model.h:179-185), 24 bytes */
 typedef struct bioem_b200_model_point
 {
@@ -125,6 +136,12 @@ int bioem_b200_synchronize(bioem_b200_handle h);
  * maps_out[nMaps]; angles_out[nOrient*nMaps] in the reference's layout
  * angle*nMaps+map (map.h:147-150), may be NULL when writeAngles == 0. */
 int bioem_b200_download(bioem_b200_handle h, bioem_b200_prob_map *maps_out, bioem_b200_prob_angle *angles_out);
+/* replaces the host heap of the WRITE_PROB_ANGLES writer (reference bioem.cpp:1254-1290):
+ * the K most probable orientations of every particle among the orientations
+ * [oBegin, oEnd), selected on the device; out[map*K + i], most probable first, in the order
+ * the reference's heap is emptied (descending (logp, orientation); a full list only takes a
+ * strictly greater logp).  Moves K*24 bytes per particle instead of nOrient*16. */
+int bioem_b200_download_top_angles(bioem_b200_handle h, int oBegin, int oEnd, int K, bioem_b200_top_angle *out);
 
 /* Multi-GPU (replaces the MPI reduction, reference bioem.cpp:909-1044).  Each GPU
  * runs a contiguous block of orientations; the per-image partial results are

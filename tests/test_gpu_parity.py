@@ -192,6 +192,66 @@ def test_angle_table_matches_oracle(setups, name):
             assert abs(lg - lo) <= atol, (m, o, lg, lo)
 
 
+def _reference_heap(logp, K):
+    """The reference's writer (bioem.cpp:1254-1290): min-heap of (logp, orientation) of size K fed in
+    orientation order, a full heap only takes a strictly greater logp; emptied -> most probable first."""
+    import heapq
+    q = []
+    for o, lp in enumerate(logp):
+        if len(q) < K:
+            heapq.heappush(q, (lp, o))
+        elif q[0][0] < lp:
+            heapq.heapreplace(q, (lp, o))
+    return [o for _, o in sorted(q, reverse=True)]
+
+
+@pytest.mark.parametrize("name,K", [("toy32", 3), ("cfg5_slice", 10), ("toy32", 40)])
+def test_top_angles_on_device_match_host_heap(setups, name, K):
+    """bioem_b200_download_top_angles == the reference's heap over the full downloaded table: same
+    orientations in the same order, rows bit-identical with the table; sub-ranges (multi-GPU blocks) too."""
+    cd, hi, parts, eng, P = setups(name)
+    eng.reset()
+    eng.run()
+    pm, pa = eng.download()
+    for o0, o1 in [(0, P.O), (P.O // 3, P.O - 1)]:
+        top = eng.download_top_angles(K, o0, o1)
+        assert top.shape == (P.M, K)
+        for m in range(P.M):
+            with np.errstate(divide="ignore"):
+                lp = np.log(pa[o0:o1, m]["forAngles"]) + pa[o0:o1, m]["ConstAngle"]
+            want = [o0 + o for o in _reference_heap(list(lp), K)]
+            got = [int(o) for o in top[m]["orient"] if o >= 0]
+            assert got == want, (m, got, want)
+            assert all(int(o) == -1 for o in top[m]["orient"][len(want):])
+            for i, o in enumerate(got):
+                assert top[m][i]["forAngles"] == pa[o, m]["forAngles"] and top[m][i]["ConstAngle"] == pa[o, m]["ConstAngle"]
+
+
+def test_top_angles_keep_the_reference_order_on_exact_ties(setups):
+    """Duplicate orientations give bit-identical rows: the list must resolve them like the heap does."""
+    cd, hi, parts, eng, P = setups("toy32")
+    e2 = api.Engine(hi.cfg)
+    try:
+        dup = np.ascontiguousarray(np.concatenate([hi.angles[:4], hi.angles[:4], hi.angles[2:6]]))
+        e2.upload_model(hi.points, hi.NormDen)
+        e2.upload_orientations(dup)
+        e2.upload_ctf(hi.refCTF, hi.CtfParam)
+        e2.upload_particles(parts)
+        e2.reset()
+        e2.run()
+        pm, pa = e2.download()
+        assert pa.shape[0] == 12
+        assert pa[0, 0]["forAngles"] == pa[4, 0]["forAngles"] and pa[0, 0]["ConstAngle"] == pa[4, 0]["ConstAngle"]
+        for K in (1, 2, 3, 5, 12, 20):
+            top = e2.download_top_angles(K)
+            for m in range(pa.shape[1]):
+                lp = np.log(pa[:, m]["forAngles"]) + pa[:, m]["ConstAngle"]
+                want = _reference_heap(list(lp), K)
+                assert [int(o) for o in top[m]["orient"] if o >= 0] == want, (K, m)
+    finally:
+        e2.close()
+
+
 def test_split_runs_accumulate_and_partials_roundtrip(setups):
     """Size-independent properties: evaluating [0,a) then [a,O) equals one call; results are
     deterministic; merging per-block results on the host equals the single run."""
