@@ -19,6 +19,7 @@
 #pragma once
 #include "fft_regs.cuh"
 #include <cstdint>
+#include <type_traits>
 #include <cuda_runtime.h>
 
 namespace bioem
@@ -763,6 +764,14 @@ template <int N> __host__ __device__ constexpr size_t lik_smem_bytes(int maxD, i
   return LikSmem<N>::bytes(lik_window_groups<N>(maxD), nwp);
 }
 
+// 64-bit shared store straight from the register pair that holds the value (with a plain C++
+// store ptxas stages five of the six row-slot stores of a column item through one register pair:
+// two MOVs each, serialised on the previous store's operand read)
+__device__ __forceinline__ void sts_f2(float2 *dst, float2 v)
+{
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"((unsigned) __cvta_generic_to_shared(dst)), "f"(v.x), "f"(v.y));
+}
+
 // 2^x, one MUFU.EX2 (results below the normal range flush to zero)
 __device__ __forceinline__ float ex2_ftz(float x)
 {
@@ -1064,7 +1073,10 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
   // The two radix passes of one column chunk (KC columns) of the current warp.
   //   col1: loads, conv * conj(particle), radix-R1, twiddle -> the warp's exchange tile
   //   col2: radix-R2 (pruned) from the tile -> row slots of Y
-  auto col1 = [&](int ch, const float4 *conv) {
+  // (FIRST: chunk 0, which also carries the Nyquist column -- a separate instance, so that the
+  // other 55 chunks do not pay the register moves that merge the two paths)
+  auto col1_ = [&](int ch, const float4 *conv, auto first_) {
+    constexpr bool FIRST = decltype(first_)::value;
     if (a_act)
     {
       float2 x[R1];
@@ -1077,16 +1089,19 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
         x[2 * n1p] = bfft::cmulc(make_float2(v.x, v.y), make_float2(r.x, r.y));
         x[2 * n1p + 1] = bfft::cmulc(make_float2(v.z, v.w), make_float2(r.z, r.w));
       }
-      if (ch == 0 && a_c == 0)
+      if constexpr (FIRST)
       {
-        // pack the Nyquist column into the (Hermitian) DC column: Z = X0 + i*X_{N/2}
-#pragma unroll
-        for (int n1p = 0; n1p < R1 / 2; n1p++)
+        if (a_c == 0)
         {
-          const float4 r = ldg4(ref + L::MAIN4 + n1p * R2 + a_n2);
-          const float4 v = ldg4(conv + L::MAIN4 + n1p * R2 + a_n2);
-          x[2 * n1p] = bfft::cadd_i(x[2 * n1p], bfft::cmulc(make_float2(v.x, v.y), make_float2(r.x, r.y)));
-          x[2 * n1p + 1] = bfft::cadd_i(x[2 * n1p + 1], bfft::cmulc(make_float2(v.z, v.w), make_float2(r.z, r.w)));
+          // pack the Nyquist column into the (Hermitian) DC column: Z = X0 + i*X_{N/2}
+#pragma unroll
+          for (int n1p = 0; n1p < R1 / 2; n1p++)
+          {
+            const float4 r = ldg4(ref + L::MAIN4 + n1p * R2 + a_n2);
+            const float4 v = ldg4(conv + L::MAIN4 + n1p * R2 + a_n2);
+            x[2 * n1p] = bfft::cadd_i(x[2 * n1p], bfft::cmulc(make_float2(v.x, v.y), make_float2(r.x, r.y)));
+            x[2 * n1p + 1] = bfft::cadd_i(x[2 * n1p + 1], bfft::cmulc(make_float2(v.z, v.w), make_float2(r.z, r.w)));
+          }
         }
       }
       bfft::Dft<R1, 1>::run(x);
@@ -1098,6 +1113,12 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
         E[k1 * ES + a_c * CS + a_n2] = x[k1];
     }
     __syncwarp();
+  };
+  auto col1 = [&](int ch, const float4 *conv) {
+    if (ch == 0)
+      col1_(ch, conv, std::true_type{});
+    else
+      col1_(ch, conv, std::false_type{});
   };
   auto col2 = [&](int ch) {
 #pragma unroll
@@ -1140,7 +1161,7 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
           float2 *Ycol = Y + k1 * YS + ch * KC + cc;
           bfft::static_for<0, NK>([&](auto j_) {
             constexpr int j = decltype(j_)::value;
-            Ycol[j * R1 * YS] = y[k2_of(j)];
+            sts_f2(Ycol + j * R1 * YS, y[k2_of(j)]);
           });
         }
       }

@@ -26,6 +26,9 @@ extern "C" cudaError_t BIOEM_CAT(bioem_lik_launch_, BIOEM_N)(const bioem::LikPar
   constexpr int HALF = L::R2 / 2;
   // radix-R2 output groups that can hold a displacement in [-maxD, maxD] (lik_window_groups)
   const int w = bioem::lik_window_groups<BIOEM_N>(maxD);
+#ifdef BIOEM_ONLY_W // experiments (tools/build_variant.py): compile a single window-group variant
+  return w == BIOEM_ONLY_W ? bioem::lik_launch_w<BIOEM_ONLY_W>(*p, nblocks, s) : cudaErrorInvalidValue;
+#else
   if (w == 1 && HALF > 1)
     return bioem::lik_launch_w<1>(*p, nblocks, s);
   if constexpr (HALF > 2)
@@ -47,4 +50,5 @@ extern "C" cudaError_t BIOEM_CAT(bioem_lik_launch_, BIOEM_N)(const bioem::LikPar
     if (w == 7)
       return bioem::lik_launch_w<7>(*p, nblocks, s);
   return bioem::lik_launch_w<HALF>(*p, nblocks, s);
+#endif
 }
