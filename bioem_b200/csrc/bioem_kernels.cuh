@@ -772,6 +772,13 @@ __device__ __forceinline__ void sts_f2(float2 *dst, float2 v)
   asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"((unsigned) __cvta_generic_to_shared(dst)), "f"(v.x), "f"(v.y));
 }
 
+__device__ __forceinline__ float rcp_approx(float x)
+{
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // 2^x, one MUFU.EX2 (results below the normal range flush to zero)
 __device__ __forceinline__ float ex2_ftz(float x)
 {
@@ -1297,27 +1304,34 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
               mn = fminf(mn, fminf(fe[j].x, fe[j].y));
             if (mn <= bfe)
             {
-              // rare: a new minimum of this thread (ties resolved by the enumeration index);
-              // what has been summed so far is re-based onto it
-              const float old = bfe;
-              bfft::static_for<0, NK>([&](auto j_) {
-                constexpr int j = decltype(j_)::value;
-                const int wy = WT[k1 + R1 * k2_of(j)];
-                const int la = wa * nw + wy, lb = la + nw;
-                if (fe[j].x < bfe || (fe[j].x == bfe && la < blin))
+              // (taken by a warp for most items: some lane has a new minimum)  Position of the item's
+              // minimum: the window index of a row grows with j (wtab: displacements 0..maxD, then
+              // -maxD..-1, both ascending in the raw row number), so scanning row wa + 1 before row wa and j
+              // downwards visits the enumeration indices in descending order -- the last match is the
+              // first in the reference's enumeration order.
+              int code = 0;
+              float vs = 0.f;
+              bfft::static_for<0, 2 * NK>([&](auto i_) {
+                constexpr int i = decltype(i_)::value;
+                constexpr int j = NK - 1 - (i % NK);
+                constexpr bool second = i < NK;
+                if ((second ? fe[j].y : fe[j].x) == mn)
                 {
-                  bfe = fe[j].x;
-                  blin = la;
-                  bv = y[k2_of(j)].x * p.invNN;
-                }
-                if (fe[j].y < bfe || (fe[j].y == bfe && lb < blin))
-                {
-                  bfe = fe[j].y;
-                  blin = lb;
-                  bv = y[k2_of(j)].y * p.invNN;
+                  code = 2 * j + (second ? 1 : 0);
+                  vs = second ? y[k2_of(j)].y : y[k2_of(j)].x;
                 }
               });
-              binv = __fdiv_rn(1.f, bfe);
+              const int jj = code >> 1;
+              const int lin = (wa + (code & 1)) * nw + WT[k1 + R1 * ((NK == R2 || jj < W) ? jj : R2 - NK + jj)];
+              const float old = bfe;
+              if (mn < bfe || (mn == bfe && lin < blin)) // ties are resolved by the enumeration index
+              {
+                bfe = mn;
+                blin = lin;
+                bv = vs * p.invNN;
+              }
+              // what has been summed so far is re-based onto the new minimum
+              binv = rcp_approx(bfe); // scales the arguments of the exp-sum only (error 1e-7 relative)
               const float sc = expa1p((old - bfe) * binv);
               S2 = __fmul2_rn(S2, make_float2(sc, sc));
             }
