@@ -1361,27 +1361,23 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
       }
 
       // ------------------------------------------------ this warp's share of the window
-      const unsigned long long best = ((unsigned long long) __float_as_uint(bfe) << 32) | (unsigned) blin;
-      unsigned long long wbest = best;
-#pragma unroll
-      for (int s = 16; s > 0; s >>= 1)
-      {
-        const unsigned long long o = shfl_xor_u64(wbest, s);
-        wbest = o < wbest ? o : wbest;
-      }
-      const float fw = __uint_as_float((unsigned) (wbest >> 32));
-      float S = (S2.x + S2.y) * expa1p((bfe - fw) * __fdiv_rn(1.f, fw));
+      // (warp-wide integer minima are single REDUX instructions; firstele is positive, so its bit
+      // pattern orders like the value)
+      const unsigned fb = __float_as_uint(bfe);
+      const unsigned long long best = ((unsigned long long) fb << 32) | (unsigned) blin;
+      const unsigned wfb = __reduce_min_sync(0xffffffffu, fb);
+      const unsigned wlin = __reduce_min_sync(0xffffffffu, fb == wfb ? (unsigned) blin : 0xffffffffu);
+      const unsigned long long wbest = ((unsigned long long) wfb << 32) | wlin;
+      const float fw = __uint_as_float(wfb);
+      float S = (S2.x + S2.y) * expa1p((bfe - fw) * rcp_approx(fw));
       // runner-up: the lowest enumeration index among the other threads' minima within 64 ulps
-      unsigned long long cand = ~0ull;
-      if (best != wbest && bfe <= __uint_as_float((unsigned) (wbest >> 32) + 64u))
-        cand = ((unsigned long long) (unsigned) blin << 32) | __float_as_uint(bfe);
+      const bool iscand = best != wbest && bfe <= __uint_as_float(wfb + 64u);
+      const unsigned cl = __reduce_min_sync(0xffffffffu, iscand ? (unsigned) blin : 0xffffffffu);
+      const unsigned cf = __reduce_min_sync(0xffffffffu, (iscand && (unsigned) blin == cl) ? fb : 0xffffffffu);
+      const unsigned long long cand = cl == 0xffffffffu ? ~0ull : (((unsigned long long) cl << 32) | cf);
 #pragma unroll
       for (int s = 16; s > 0; s >>= 1)
-      {
         S += __shfl_xor_sync(0xffffffffu, S, s);
-        const unsigned long long o = shfl_xor_u64(cand, s);
-        cand = o < cand ? o : cand;
-      }
       if (best == wbest)
         s_wv[slot][warp] = bv;
       if (lane == 0)
