@@ -108,6 +108,13 @@ def test_binary_multi_gpu_split_equals_single(tmp_path):
         np.testing.assert_allclose(a["logp"], b["logp"], atol=2e-4)
         for k in ("cent_x", "cent_y", "angles", "env", "defocus"):
             np.testing.assert_array_equal(a[k], b[k])
+        # WRITE_PROB_ANGLES: every GPU keeps its block's most probable orientations, the host merges them
+        o1, o2 = tmp_path / "ang1", tmp_path / "ang2"
+        o1.mkdir()
+        o2.mkdir()
+        _run("toy32", o1, env={"BIOEM_B200_GPUS": "1"})
+        _run("toy32", o2, env={"BIOEM_B200_GPUS": "2"})
+        assert open(o1 / "ANG_PROB").read() == open(o2 / "ANG_PROB").read()
 
 
 REF_CUDA = os.path.join(ROOT, "oracle", "_ref", "bioEM_ref_cuda")
