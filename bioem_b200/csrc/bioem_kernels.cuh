@@ -1178,6 +1178,10 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
   // pass 1 of this warp's first column chunk was already run behind the closing barrier of the
   // previous likelihood
   bool pre_done = false;
+  // first column chunk of this warp.  Chunk 0 (which also carries the Nyquist column: half as many
+  // loads and multiplies again) goes to the last warp, which has the fewest row tasks: its first
+  // radix pass runs in that warp's slack before the closing barrier.
+  const int ch0 = (warp + 1) % NWARP;
 
   for (int ol = o_lo; ol < o_hi; ol++)
   {
@@ -1200,9 +1204,9 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
       const float f_d = __fmul_rn(__fmul_rn(sR, sR), cp.sumsqC);
 
       // ------------------------------------------------ column pass (along kx), per warp
-      for (int ch = warp; ch < NCH; ch += NWARP)
+      for (int ch = ch0; ch < NCH; ch += NWARP)
       {
-        if (!(pre_done && ch == warp))
+        if (!(pre_done && ch == ch0))
           col1(ch, conv);
         col2(ch);
       }
@@ -1393,9 +1397,9 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
       __syncwarp();
       if (lane == 0)
         asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(mbar_addr) : "memory");
-      if (warp < NCH && oc + 1 < o_hi * p.C)
+      if (ch0 < NCH && oc + 1 < o_hi * p.C)
       {
-        col1(warp, conv + L::MAP4); // the next conv spectrum of the batch follows this one
+        col1(ch0, conv + L::MAP4); // the next conv spectrum of the batch follows this one
         pre_done = true;
       }
       {
