@@ -1406,10 +1406,12 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
         unsigned done;
         do
         {
-          asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2;\n\t"
+          // (with a suspend-time hint: the warp sleeps in the barrier unit instead of spinning through
+          // the issue slots of the other three warps of its scheduler)
+          asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2, %3;\n\t"
                        "selp.u32 %0, 1, 0, p;\n\t}"
                        : "=r"(done)
-                       : "r"(mbar_addr), "r"(mbar_parity)
+                       : "r"(mbar_addr), "r"(mbar_parity), "r"(0x989680u)
                        : "memory");
         } while (!done);
         mbar_parity ^= 1u;
