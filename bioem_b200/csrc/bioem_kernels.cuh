@@ -830,10 +830,11 @@ struct BookState
 //     reference operation order, two displacements per packed instruction) straight out of
 //     the FFT registers; every thread keeps an ONLINE (min firstele <=> max logpro, its
 //     enumeration index and correlation value, sum of exp relative to that minimum, re-based
-//     when the minimum moves); warp shuffles combine the lanes into one ring entry per warp,
+//     when the minimum moves); REDUX minima and a shuffle sum combine the lanes into one ring
+//     entry per warp,
 //   * the bookkeeping (double-precision log, float narrowing, first-of-ties rule over the
 //     near-minimum candidates, log-sum-exp fold into the image's running state) is deferred:
-//     warp 0 does it for up to 32 likelihoods at once, one per lane.
+//     warp 0 does it for lik_pending<N>() = 16 likelihoods at once, one per lane.
 // All butterflies run on packed FP32x2 instructions.  Per likelihood one CTA barrier (columns
 // -> rows) and one split-phase mbarrier (rows -> next columns: arrive, run the first radix pass
 // of the next likelihood's first chunk, wait); no correlation map ever leaves the SM.
