@@ -736,6 +736,12 @@ template <int N> __host__ __device__ constexpr int lik_warps()
 #ifdef BIOEM_LW
   return BIOEM_LW;
 #else
+  // small images: four CTAs of 4 warps per SM -- the row slots are small, and the finer barrier
+  // domains lose less to the uneven last round of row tasks (measured with the N/4 window:
+  // N = 64 8.0 -> 6.1, N = 96 19.1 -> 15.5, N = 128 27.6 -> 23.0 ns/likelihood; N = 160 / 192 are
+  // slower that way, their row slots allow only two or three such CTAs)
+  if (N <= 128)
+    return 4;
   if (N <= 224)
     return 8;
   constexpr size_t budget = 227 * 1024 - 1024;
