@@ -314,7 +314,7 @@ BFFT_GEO(32, 4, 8, 16, 16)
 BFFT_GEO(36, 6, 6, 18, 16)
 BFFT_GEO(48, 6, 8, 12, 16)
 BFFT_GEO(64, 8, 8, 16, 16)
-BFFT_GEO(96, 8, 12, 16, 16)
+BFFT_GEO(96, 12, 8, 16, 16)
 BFFT_GEO(128, 8, 16, 16, 16)
 BFFT_GEO(160, 10, 16, 16, 16)
 BFFT_GEO(192, 12, 16, 16, 16)
