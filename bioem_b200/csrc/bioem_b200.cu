@@ -651,8 +651,9 @@ static int ensure_batch(bioem_b200_context *h)
   if (getenv("BIOEM_B200_OB"))
     ob = std::max<long>(1, std::min<long>(atol(getenv("BIOEM_B200_OB")), h->O));
   h->OB = (int) ob;
-  // orientations per CTA: amortise the CTA prologue when there are few CTFs, keep >= 4 waves
-  int og = std::max(1, (16 + h->C - 1) / h->C);
+  // orientations per CTA: amortise the CTA prologue (and the one likelihood per CTA whose first radix pass
+  // cannot be run ahead) over >= 64 likelihoods, keep >= 4 waves (cfg2: 1 -> 2 orientations, +0.5 %)
+  int og = std::max(1, (64 + h->C - 1) / h->C);
   while (og > 1 && (long long) h->M * ((h->OB + og - 1) / og) < 4LL * 296)
     og--;
   if (getenv("BIOEM_B200_OG"))
