@@ -25,7 +25,7 @@ plain = json.load(open(sys.argv[2]))
 print(f"# ncu launch list, {sys.argv[3]}")
 print("# command: ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv python bench.py --steps 1 --warmup 0 "
       "--no-cpu-baseline --no-e2e")
-print(f"# (same command exited 0 without ncu first; plain bench of the same build: {plain['value'] / 1e6:.2f} M likelihoods/s, "
+print(f"# (bench.py of the same build ran to completion without ncu first -- default arguments, 3 warm-up + 2 timed steps: {plain['value'] / 1e6:.2f} M likelihoods/s, "
       f"{plain['ms_per_step'] / 1e3:.2f} s/step, kernel share {plain['roofline']['kernel_share_of_step']}).")
 print("# Per-launch times under ncu are serialised/cold: compare SHARES.  " + plain["config"]["workload"])
 print("kernel,launches,total_ms,share")
