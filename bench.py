@@ -136,9 +136,9 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # stdout carries exactly one JSON line: NCCL's own output (the version banner it prints at
+        # NCCL_DEBUG=VERSION / WARN, warnings) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     cd, hi, parts = build_workload(args.workload)
