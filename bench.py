@@ -138,6 +138,9 @@ def run_ours(args):
     if world > 1:
         # stdout carries exactly one JSON line: NCCL's own output (the version banner it prints at
         # NCCL_DEBUG=VERSION / WARN, warnings) goes to stderr
+        # (NCCL honours NCCL_DEBUG_FILE only above the VERSION level)
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "NONE", ""):
+            os.environ["NCCL_DEBUG"] = "WARN"
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
