@@ -653,7 +653,9 @@ static int ensure_batch(bioem_b200_context *h)
   h->OB = (int) ob;
   // orientations per CTA: amortise the CTA prologue (and the one likelihood per CTA whose first radix pass
   // cannot be run ahead) over >= 64 likelihoods, keep >= 4 waves (cfg2: 1 -> 2 orientations, +0.5 %)
-  int og = std::max(1, (64 + h->C - 1) / h->C);
+  // (above N = 224, one CTA per SM, more than one orientation per CTA at 32 CTFs costs 3-5 %)
+  const int per_cta = h->N <= 224 ? 64 : 16;
+  int og = std::max(1, (per_cta + h->C - 1) / h->C);
   while (og > 1 && (long long) h->M * ((h->OB + og - 1) / og) < 4LL * 296)
     og--;
   if (getenv("BIOEM_B200_OG"))
