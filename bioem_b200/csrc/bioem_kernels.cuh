@@ -721,11 +721,11 @@ template <int N> struct LikGeo
 };
 template <int N> __host__ __device__ constexpr int lik_window_groups(int maxD);
 
-// likelihoods whose double-precision bookkeeping is deferred, then done by up to 32 lanes at once
-// (16 where a single CTA already needs nearly all of the shared memory)
+// likelihoods whose double-precision bookkeeping is deferred, then done by that many lanes of warp 0
+// at once (16: the ring of a CTA fits next to the row slots and exchange tiles at every size)
 template <int N> __host__ __device__ constexpr int lik_pending() { return 16; }
 
-// warps per CTA of the fused kernel.  Up to N = 224 two CTAs of 8 warps share an SM.  Measured
+// warps per CTA of the fused kernel.  From N = 160 to 224 two CTAs of 8 warps share an SM.  Measured
 // on B200 at N = 224 (tools/build_variant.py): 8 warps 55.1 ns/likelihood, 7 warps (which would
 // divide both the 56 column chunks and the 21 row tasks evenly) 58.1 ns -- registers are granted
 // in units of 4 warps, so 7 warps buy nothing.  Above, one CTA fills the SM (its row slots need
