@@ -8,7 +8,7 @@
 //
 // Parity pinning: this restatement is itself checked against the UNMODIFIED
 // reference built from /root/reference (oracle/_ref/bioEM_ref, see Makefile) in
-// tests/test_oracle_vs_reference.py, both on the final Output_Probabilities and on
+// tests/test_oracle.py, both on the final Output_Probabilities and on
 // the per-evaluation -DDEBUG_PROB stream (bioem_algorithm.h:88-128), and against
 // the golden outputs of that binary committed under tests/golden/.
 //
