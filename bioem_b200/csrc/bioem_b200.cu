@@ -656,7 +656,8 @@ static int ensure_batch(bioem_b200_context *h)
   // (above N = 224, one CTA per SM, more than one orientation per CTA at 32 CTFs costs 3-5 %)
   const int per_cta = h->N <= 224 ? 64 : 16;
   int og = std::max(1, (per_cta + h->C - 1) / h->C);
-  while (og > 1 && (long long) h->M * ((h->OB + og - 1) / og) < 4LL * 296)
+  const long long cta_slots = h->N <= 128 ? 592 : h->N <= 224 ? 296 : 148; // resident CTAs of the fused kernel per GPU
+  while (og > 1 && (long long) h->M * ((h->OB + og - 1) / og) < 4LL * cta_slots)
     og--;
   if (getenv("BIOEM_B200_OG"))
     og = std::max(1, atoi(getenv("BIOEM_B200_OG")));
