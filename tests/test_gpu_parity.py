@@ -312,6 +312,49 @@ def test_recovers_planted_parameters(setups):
     assert hit >= P.M - 2, (pm["orient"], cd.truth[:, 0])
 
 
+def test_headline_shape_properties():
+    """BASELINE configs[1] shape (1000 particles of 224 x 224, production CTF grid and window) on 340
+    orientations -- more than two launches of the fused kernel, an odd tail of the two-orientation groups --
+    through size-independent properties (the oracle would need hours here): bit-determinism, a split at an
+    unaligned orientation equals one call, eight rank blocks merged on the host equal the single run, and the
+    planted orientation / CTF / displacement of the synthetic particles is what the arg-max finds."""
+    _need_gpu()
+    cd = build_case("cfg2", n_particles=1000, n_orient=340)
+    hi, parts = api.inputs_for_case(cd)
+    eng = api.Engine(hi.cfg)
+    try:
+        eng.upload_all(hi, parts)
+        O = 340
+        eng.reset()
+        eng.run()
+        full, _ = eng.download()
+        eng.reset()
+        eng.run()
+        again, _ = eng.download()
+        assert full.tobytes() == again.tobytes()
+        assert np.isfinite(full["Total"]).all() and (full["Total"] > 0).all() and np.isfinite(full["Constoadd"]).all()
+        eng.reset()
+        eng.run(0, 101)
+        eng.run(101, O)
+        split, _ = eng.download()
+        np.testing.assert_allclose(split["Total"], full["Total"], rtol=1e-12)
+        for k in ("Constoadd", "cent_x", "cent_y", "orient", "conv", "norm", "mu"):
+            np.testing.assert_array_equal(split[k], full[k])
+        blocks = []
+        for r in range(8):  # the reference's MPI split, bioem.cpp:748-753
+            eng.reset()
+            eng.run(r * O // 8, (r + 1) * O // 8)
+            blocks.append(eng.download()[0])
+        merged = api.merge_host(np.stack(blocks))
+        np.testing.assert_allclose(merged["Total"], full["Total"], rtol=1e-12)
+        for k in ("Constoadd", "cent_x", "cent_y", "orient", "conv", "norm", "mu"):
+            np.testing.assert_array_equal(merged[k], full[k])
+        hit = int((full["orient"] == cd.truth[:, 0].astype(int)).sum())
+        assert hit >= 950, hit
+    finally:
+        eng.close()
+
+
 def test_mrc_ingest_on_device_matches_host_reader(setups):
     """§8 f2: an MRC stack handed over in file order (upload_particles_mrc: transposition and
     normalisation with float accumulators in file order ON THE DEVICE, reference map.cpp:811-845)
