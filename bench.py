@@ -257,6 +257,10 @@ def run_ours(args):
                     "avg_launch_ms": round(lik_ms / lik_launches, 3),
                     "algorithmic_bytes_per_likelihood": 8 * F,
                     "fp32_algorithmic_tflops": round(per_rank_lik * flop / (lik_ms / 1e3) / 1e12, 2),
+                    # compute side of the two-sided FFT roofline: 148 SMs x 128 FP32 lanes x 2 x SM clock
+                    "fp32_peak_tflops": round(148 * 128 * 2 * (clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0) / 1e6, 1),
+                    "fp32_frac": round(per_rank_lik * flop / (lik_ms / 1e3) / 1e12
+                                       / (148 * 128 * 2 * (clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0) / 1e6), 4),
                     "kernel_share_of_step": round(lik_ms / (ms_total), 4)}
         line = {
             "metric": "likelihoods/s", "value": round(value, 1), "unit": "likelihoods/s",
