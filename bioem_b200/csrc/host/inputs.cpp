@@ -642,6 +642,21 @@ void read_model(const Options &o, const Params &p, std::vector<bioem_b200_model_
       fail("Reading model dump");
     fclose(f);
     std::cout << "Protein structure read from model dump\n";
+    // like the reference, a dump holds the model as read: it is centred after loading, with the
+    // NormDen stored in the dump (model.cpp:676-707, 604-672)
+    if (!p.nocentermass)
+    {
+      float cm[3] = {0.f, 0.f, 0.f};
+      for (const auto &pt : pts)
+        for (int k = 0; k < 3; k++)
+          cm[k] += pt.pos[k] * pt.density;
+      for (int k = 0; k < 3; k++)
+        cm[k] /= NormDen;
+      for (auto &pt : pts)
+        for (int k = 0; k < 3; k++)
+          pt.pos[k] -= cm[k];
+    }
+    std::cout << "Total Number of Voxels " << pts.size() << "\nEffective number of electrons " << NormDen << "\n";
     return;
   }
   const char *name = o.modelfile.c_str();
@@ -757,17 +772,9 @@ void read_model(const Options &o, const Params &p, std::vector<bioem_b200_model_
   }
   if (pts.empty())
     fail("No model points read from %s", name);
-  // centre of density unless NO_CENTEROFMASS, and NormDen (model.cpp:229-234,604-672,704-707)
-  NormDen = bioem_b200_host_model_prepare(pts.data(), (int) pts.size(), p.nocentermass ? 0 : 1);
-  std::cout << "Total Number of Voxels " << pts.size() << "\nEffective number of electrons " << NormDen << "\n";
-  if (o.printCoordRead)
-  {
-    std::ofstream out("COORDREAD");
-    out.precision(4);
-    out.setf(std::ios::fixed);
-    for (const auto &pt : pts)
-      out << "COOR " << pt.pos[0] << " " << pt.pos[1] << " " << pt.pos[2] << " " << pt.radius << " " << pt.density << "\n";
-  }
+  // NormDen; --DumpModel writes the model as read, before the centring (model.cpp:695-698); then the centre of
+  // density unless NO_CENTEROFMASS (model.cpp:229-234,604-672,704-707)
+  NormDen = bioem_b200_host_model_prepare(pts.data(), (int) pts.size(), 0);
   if (o.dumpModel)
   {
     FILE *f = fopen("model.dump", "wb");
@@ -778,6 +785,16 @@ void read_model(const Options &o, const Params &p, std::vector<bioem_b200_model_
     fwrite(&n, sizeof(int), 1, f);
     fwrite(pts.data(), sizeof(bioem_b200_model_point), n, f);
     fclose(f);
+  }
+  NormDen = bioem_b200_host_model_prepare(pts.data(), (int) pts.size(), p.nocentermass ? 0 : 1);
+  std::cout << "Total Number of Voxels " << pts.size() << "\nEffective number of electrons " << NormDen << "\n";
+  if (o.printCoordRead)
+  {
+    std::ofstream out("COORDREAD");
+    out.precision(4);
+    out.setf(std::ios::fixed);
+    for (const auto &pt : pts)
+      out << "COOR " << pt.pos[0] << " " << pt.pos[1] << " " << pt.pos[2] << " " << pt.radius << " " << pt.density << "\n";
   }
 }
 

@@ -200,3 +200,56 @@ def test_host_binary_orientation_grids_and_errors(tmp_path):
     assert len(pts) == 2
     assert np.allclose(pts["pos"], [[12, 14, 3], [-2, 4, -6]])
     assert np.allclose(pts["radius"], [2.25, 3.4]) and np.allclose(pts["density"], [40, 108])
+
+
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "bioEM_ref")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="reference binary not built (oracle/_ref)")
+@pytest.mark.parametrize("name", ["toy32", "toy36g2"])
+def test_dump_caches_are_interchangeable_with_the_reference(name, tmp_path):
+    """--DumpModel / --DumpMaps / --LoadModelDump / --LoadMapDump (reference model.cpp:41-82,676-707,
+    map.cpp:44-78): the binary caches have the reference's layout and meaning -- the model as read (before
+    the centring, which is redone after loading), the particles as the reader leaves them -- so a cache
+    written by the unmodified reference loads into bioEM_b200 and gives the arrays a direct read gives."""
+    import subprocess
+    from bioem_b200.cases import reference_cli
+    exe = _build_host_bin()
+    cd = build_case(name, str(tmp_path))
+    cli = reference_cli(cd)
+    ref_dir, our_dir, direct, loaded = (tmp_path / d for d in ("ref", "ours", "direct", "loaded"))
+    for d in (ref_dir, our_dir, direct, loaded):
+        d.mkdir()
+    r = subprocess.run([REF_BIN] + cli + ["--DumpModel", "--DumpMaps"], cwd=ref_dir, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-400:] + r.stderr[-400:]
+    r = subprocess.run([exe] + cli + ["--DumpModel", "--DumpMaps"], cwd=our_dir, capture_output=True, text=True,
+                       env={**os.environ, "BIOEM_B200_DUMP_INPUTS": str(direct)})
+    assert r.returncode == 0, r.stdout[-400:] + r.stderr[-400:]
+    # model.dump: float NormDen, int n, n x 24-byte points
+    a, b = (open(d / "model.dump", "rb").read() for d in (ref_dir, our_dir))
+    assert len(a) == len(b) and a[4:8] == b[4:8]
+    nd_ref, nd_our = np.frombuffer(a[:4], "<f4")[0], np.frombuffer(b[:4], "<f4")[0]
+    assert abs(nd_ref - nd_our) <= 4e-7 * abs(nd_ref)  # the reference sums the densities per reader thread, -ffast-math
+    pa, pb = (np.frombuffer(x[8:], "<f4").reshape(-1, 6) for x in (a, b))
+    for col in (0, 1, 2, 4, 5):  # pos[3], radius, density (column 3 is the unused quat4 of the point struct)
+        assert pa[:, col].tobytes() == pb[:, col].tobytes(), col
+    # maps.dump: int nMaps, nMaps x N x N floats; MRC stacks are normalised by the reader, where the
+    # reference's -ffast-math build rounds differently in the last place (quirk Q7)
+    a, b = (open(d / "maps.dump", "rb").read() for d in (ref_dir, our_dir))
+    assert len(a) == len(b) and a[:4] == b[:4]
+    ma, mb = (np.frombuffer(x[4:], "<f4") for x in (a, b))
+    if cd.case.particle_format == "text":
+        assert ma.tobytes() == mb.tobytes()
+    else:
+        np.testing.assert_allclose(mb, ma, rtol=0, atol=2.5e-7 * np.abs(ma).max())
+    # load the REFERENCE's caches: same arrays as the direct read (model centred after loading)
+    r = subprocess.run([exe] + cli + ["--LoadModelDump", "--LoadMapDump"], cwd=ref_dir, capture_output=True, text=True,
+                       env={**os.environ, "BIOEM_B200_DUMP_INPUTS": str(loaded)})
+    assert r.returncode == 0, r.stdout[-400:] + r.stderr[-400:]
+    p_direct = np.fromfile(direct / "points.bin", dtype=api.MODEL_POINT_DTYPE)
+    p_loaded = np.fromfile(loaded / "points.bin", dtype=api.MODEL_POINT_DTYPE)
+    np.testing.assert_allclose(p_loaded["pos"], p_direct["pos"], rtol=0, atol=2e-6)
+    assert np.array_equal(p_loaded["radius"], p_direct["radius"]) and np.array_equal(p_loaded["density"], p_direct["density"])
+    m_direct = np.fromfile(direct / "maps.bin", dtype=np.float32)
+    m_loaded = np.fromfile(loaded / "maps.bin", dtype=np.float32)
+    np.testing.assert_allclose(m_loaded, m_direct, rtol=0, atol=2.5e-7 * np.abs(m_direct).max())
