@@ -625,6 +625,17 @@ static bool has_ext(const std::string &s, const char *ext)
   return found != std::string::npos && found <= end;
 }
 
+// --PrintCOORDREAD: the (centred) model as the reference lists it (model.cpp:712-740)
+static void print_coordread(const std::vector<bioem_b200_model_point> &pts)
+{
+  std::cout << "Note - Look at file COORDREAD to confirm that the Model coordinates are correct\n";
+  std::ofstream out("COORDREAD");
+  out << "Text --- Number ---- x ---- y ---- z ---- radius ---- number of electron\n";
+  for (size_t n = 0; n < pts.size(); n++)
+    out << "RESIDUE " << n << " " << pts[n].pos[0] << " " << pts[n].pos[1] << " " << pts[n].pos[2] << " " << pts[n].radius
+        << " " << pts[n].density << "\n";
+}
+
 void read_model(const Options &o, const Params &p, std::vector<bioem_b200_model_point> &pts, float &NormDen)
 {
   pts.clear();
@@ -657,6 +668,8 @@ void read_model(const Options &o, const Params &p, std::vector<bioem_b200_model_
           pt.pos[k] -= cm[k];
     }
     std::cout << "Total Number of Voxels " << pts.size() << "\nEffective number of electrons " << NormDen << "\n";
+    if (o.printCoordRead)
+      print_coordread(pts);
     return;
   }
   const char *name = o.modelfile.c_str();
@@ -789,13 +802,7 @@ void read_model(const Options &o, const Params &p, std::vector<bioem_b200_model_
   NormDen = bioem_b200_host_model_prepare(pts.data(), (int) pts.size(), p.nocentermass ? 0 : 1);
   std::cout << "Total Number of Voxels " << pts.size() << "\nEffective number of electrons " << NormDen << "\n";
   if (o.printCoordRead)
-  {
-    std::ofstream out("COORDREAD");
-    out.precision(4);
-    out.setf(std::ios::fixed);
-    for (const auto &pt : pts)
-      out << "COOR " << pt.pos[0] << " " << pt.pos[1] << " " << pt.pos[2] << " " << pt.radius << " " << pt.density << "\n";
-  }
+    print_coordread(pts);
 }
 
 // --------------------------------------------------------------------------- particles

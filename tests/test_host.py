@@ -220,11 +220,19 @@ def test_dump_caches_are_interchangeable_with_the_reference(name, tmp_path):
     ref_dir, our_dir, direct, loaded = (tmp_path / d for d in ("ref", "ours", "direct", "loaded"))
     for d in (ref_dir, our_dir, direct, loaded):
         d.mkdir()
-    r = subprocess.run([REF_BIN] + cli + ["--DumpModel", "--DumpMaps"], cwd=ref_dir, capture_output=True, text=True)
+    r = subprocess.run([REF_BIN] + cli + ["--DumpModel", "--DumpMaps", "--PrintCOORDREAD"], cwd=ref_dir,
+                       capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-400:] + r.stderr[-400:]
-    r = subprocess.run([exe] + cli + ["--DumpModel", "--DumpMaps"], cwd=our_dir, capture_output=True, text=True,
+    r = subprocess.run([exe] + cli + ["--DumpModel", "--DumpMaps", "--PrintCOORDREAD"], cwd=our_dir, capture_output=True, text=True,
                        env={**os.environ, "BIOEM_B200_DUMP_INPUTS": str(direct)})
     assert r.returncode == 0, r.stdout[-400:] + r.stderr[-400:]
+    # COORDREAD (model.cpp:712-740): same lines, the centred coordinates to the last printed digit or one off
+    la, lb = (open(d / "COORDREAD").read().split("\n") for d in (ref_dir, our_dir))
+    assert len(la) == len(lb) and la[0] == lb[0]
+    for x, y in zip(la[1:], lb[1:]):
+        tx, ty = x.split(), y.split()
+        assert len(tx) == len(ty) and tx[:2] == ty[:2]
+        assert all(abs(float(u) - float(v)) <= 2e-6 * max(1.0, abs(float(u))) for u, v in zip(tx[2:], ty[2:])), (x, y)
     # model.dump: float NormDen, int n, n x 24-byte points
     a, b = (open(d / "model.dump", "rb").read() for d in (ref_dir, our_dir))
     assert len(a) == len(b) and a[4:8] == b[4:8]
