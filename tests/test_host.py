@@ -261,3 +261,42 @@ def test_dump_caches_are_interchangeable_with_the_reference(name, tmp_path):
     m_direct = np.fromfile(direct / "maps.bin", dtype=np.float32)
     m_loaded = np.fromfile(loaded / "maps.bin", dtype=np.float32)
     np.testing.assert_allclose(m_loaded, m_direct, rtol=0, atol=2.5e-7 * np.abs(m_direct).max())
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="reference binary not built (oracle/_ref)")
+@pytest.mark.parametrize("tag,extra,ncol", [("euler", "GRIDPOINTS_ALPHA 4\nGRIDPOINTS_BETA 3\n", 3),
+                                            ("quat2", "USE_QUATERNIONS\nGRIDPOINTS_QUATERNION 2\n", 4),
+                                            ("quat3", "USE_QUATERNIONS\nGRIDPOINTS_QUATERNION 3\n", 4)])
+def test_orientation_grids_match_the_reference_binary(tag, extra, ncol, tmp_path):
+    """Euler / quaternion grid generators (param.cpp:1009-1048,1141-1210) against the unmodified reference:
+    with WRITE_PROB_ANGLES = number of orientations its ANG_PROB lists every orientation of the grid (4
+    decimals); the multiset of rows must be the grid bioEM_b200 hands to the library."""
+    import collections
+    import subprocess
+    exe = _build_host_bin()
+    cd = build_case("toy32", str(tmp_path))
+    common = ("PIXEL_SIZE 1.5\nNUMBER_PIXELS 32\nDISPLACE_CENTER 4 1\nCTF_DEFOCUS 1.0 4.0 3\n"
+              "CTF_B_ENV 2.0 300.0 1\nCTF_AMPLITUDE 0.1 0.1 1\n")
+    base = ["--Modelfile", cd.paths["model"], "--Particlesfile", cd.paths["particles"], "--Inputfile", "p.txt"]
+    hook = tmp_path / "hook"
+    hook.mkdir()
+    (tmp_path / "p.txt").write_text(common + extra)
+    r = subprocess.run([exe] + base, cwd=tmp_path, capture_output=True, text=True,
+                       env={**os.environ, "BIOEM_B200_DUMP_INPUTS": str(hook)})
+    assert r.returncode == 0, r.stderr[-400:]
+    ang = np.fromfile(hook / "angles.bin", dtype=np.float32).reshape(-1, 4).astype(np.float64)
+    (tmp_path / "p.txt").write_text(common + extra + f"WRITE_PROB_ANGLES {len(ang)}\n")
+    r = subprocess.run([REF_BIN] + base, cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-400:] + r.stderr[-400:]
+    rows = []
+    for ln in open(tmp_path / "ANG_PROB").read().split("\n"):
+        t = ln.split()
+        if len(t) > 6 and t[0] == "0" and "Separated:" in t:
+            rows.append(tuple(float(x) for x in t[1:1 + ncol]))
+
+    def norm(row):  # "-0.0000" and "0.0000" are the same angle
+        return tuple(0.0 if abs(v) < 5e-5 else v for v in row)
+
+    mine = [tuple(float(f"{v:.4f}") for v in a[:ncol]) for a in ang]
+    assert len(rows) == len(mine)
+    assert collections.Counter(map(norm, rows)) == collections.Counter(map(norm, mine))
