@@ -34,6 +34,8 @@ class Case:
     model_sigma: float = 18.0
     model_rmax: float = 45.0
     particle_format: str = "text"   # "text" | "mrc"
+    extra: tuple = ()               # further parameter-file lines (optional keywords)
+    angle_priors: bool = False      # PRIOR_ANGLES: a fifth column (log prior) in the orientation list
 
     @property
     def use_psf(self) -> bool:
@@ -58,6 +60,13 @@ CASES = {
     # edge windows: a single displacement, and the largest window the image allows
     "toy32d0": Case("toy32d0", 32, 1.5, 60, 3, 576, 12, CFG1_CTF, 0, 1, model_sigma=5.0, model_rmax=12.0),
     "toy32full": Case("toy32full", 32, 1.5, 60, 3, 576, 6, CFG1_CTF, 15, 1, model_sigma=5.0, model_rmax=12.0),
+    # optional keywords of the parameter file in one case: sphere-footprint shift, model prior, no centring,
+    # another electron wavelength, amplitude prior, per-orientation priors from the orientation list
+    "toy32opts": Case("toy32opts", 32, 1.5, 60, 3, 576, 20, CFG1_CTF, 4, 1, write_angles=4, model_sigma=5.0,
+                      model_rmax=12.0, extra=("SHIFT_X 1", "SHIFT_Y -1", "PRIOR_MODEL 0.25", "NO_CENTEROFMASS",
+                                              "ELECTRON_WAVELENGTH 0.0251", "SIGMA_PRIOR_AMP_CTF 0.3",
+                                              "PRIOR_AMP_CTF_CENTER 0.1", "SIGMA_PRIOR_DEFOCUS 1.5"),
+                      angle_priors=True),
     "toy36g2": Case("toy36g2", 36, 1.5, 60, 4, 576, 16, CFG1_CTF, 6, 2, model_sigma=6.0,
                     model_rmax=14.0, particle_format="mrc"),
     "toy64": Case("toy64", 64, 1.5, 200, 5, 576, 32, synth.PRODUCTION_GRID, 10, 1,
@@ -112,10 +121,15 @@ def build_case(name_or_case, outdir: str | None = None, n_particles: int | None 
                      particles=os.path.join(outdir, "particles.mrc" if c.particle_format == "mrc"
                                             else "particles.txt"))
         synth.write_model_text(paths["model"], model)
+        extra = list(c.extra) + (["USE_PSF", "WRITE_CTF_PARAM 1"] if c.use_psf else []) + \
+            (["PRIOR_ANGLES"] if c.angle_priors else [])
         synth.write_param_file(paths["param"], c.n_pixels, c.pixel_size, c.max_disp, c.grid_space,
-                               c.ctf, True, c.write_angles,
-                               extra=["USE_PSF", "WRITE_CTF_PARAM 1"] if c.use_psf else None)
-        synth.write_orientation_list(paths["orient"], quats)
+                               c.ctf, True, c.write_angles, extra=extra or None)
+        if c.angle_priors:  # log priors -0.5, -0.25, 0, ... per orientation (exact in the 12-column format)
+            pri = (-0.5 + 0.25 * (np.arange(len(quats)) % 5)).astype(np.float32)
+            synth.write_orientation_list(paths["orient"], np.concatenate([quats, pri[:, None]], axis=1))
+        else:
+            synth.write_orientation_list(paths["orient"], quats)
         if c.particle_format == "mrc":
             synth.write_particles_mrc(paths["particles"], imgs)
         else:

@@ -30,7 +30,7 @@ def _run(name, tmp_path, env=None):
     return cd
 
 
-@pytest.mark.parametrize("name", ["toy32", "toy32psf", "toy64", "cfg1", "cfg2_slice"])
+@pytest.mark.parametrize("name", ["toy32", "toy32psf", "toy32opts", "toy64", "cfg1", "cfg2_slice"])
 def test_binary_output_probabilities_match_reference_golden(name, tmp_path, golden_dir):
     cd = _run(name, tmp_path)
     got_path = tmp_path / "Output_Probabilities"
@@ -72,19 +72,24 @@ def _is_number(tok):
         return False
 
 
-def test_binary_ang_prob_matches_reference_golden(tmp_path, golden_dir):
+@pytest.mark.parametrize("name", ["toy32", "toy32opts"])
+def test_binary_ang_prob_matches_reference_golden(name, tmp_path, golden_dir):
     """WRITE_PROB_ANGLES: same header, same number of rows per image, same top orientation and
-    log-probabilities within tolerance (the order further down the list may swap on near-ties)."""
-    _run("toy32", tmp_path)
+    log-probabilities within tolerance (the order further down the list may swap on near-ties).
+    toy32opts adds PRIOR_ANGLES: the rows are ordered without the prior, which is printed and added last."""
+    _run(name, tmp_path)
     got = open(tmp_path / "ANG_PROB").read().split("\n")
-    ref = open(os.path.join(golden_dir, "toy32", "ANG_PROB")).read().split("\n")
+    ref = open(os.path.join(golden_dir, name, "ANG_PROB")).read().split("\n")
     assert got[:3] == ref[:3] and len(got) == len(ref)
     g = np.array([[float(x) for x in ln.replace("Separated:", "").split()] for ln in got[3:] if ln.strip()])
     r = np.array([[float(x) for x in ln.replace("Separated:", "").split()] for ln in ref[3:] if ln.strip()])
     assert g.shape == r.shape
     for m in np.unique(r[:, 0]):
         gm, rm = g[g[:, 0] == m], r[r[:, 0] == m]
-        assert np.all(np.diff(gm[:, 5]) <= 1e-9)  # descending log-probability
+        key = gm[:, 5] - (gm[:, 9] if gm.shape[1] > 9 else 0.0)
+        assert np.all(np.diff(key) <= 1e-3)  # descending log-probability (before the angle prior, 4 decimals)
+        if gm.shape[1] > 9:
+            np.testing.assert_array_equal(gm[:, 9], rm[:, 9])
         np.testing.assert_allclose(gm[:, 5], rm[:, 5], atol=5e-3 + 1e-4)
         # same set of orientations up to swaps between near-equal entries
         gs = {tuple(np.round(x, 3)) for x in gm[:, 1:5]}
