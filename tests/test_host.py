@@ -300,3 +300,39 @@ def test_orientation_grids_match_the_reference_binary(tag, extra, ncol, tmp_path
     mine = [tuple(float(f"{v:.4f}") for v in a[:ncol]) for a in ang]
     assert len(rows) == len(mine)
     assert collections.Counter(map(norm, rows)) == collections.Counter(map(norm, mine))
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="reference binary not built (oracle/_ref)")
+def test_multiple_mrc_list_matches_the_reference_binary(tmp_path):
+    """--ReadMRC --ReadMultipleMRC (map.cpp:196-243): a text file naming several MRC stacks; the particles must
+    come out in the reference's order and normalisation (its maps.dump is the witness)."""
+    import subprocess
+    from bioem_b200 import synth
+    exe = _build_host_bin()
+    cd = build_case("toy36g2", str(tmp_path))
+    imgs = cd.particles
+    synth.write_particles_mrc(str(tmp_path / "a.mrc"), imgs[:3])
+    synth.write_particles_mrc(str(tmp_path / "b.mrc"), imgs[3:])
+    (tmp_path / "list.txt").write_text(f"{tmp_path / 'a.mrc'}\n{tmp_path / 'b.mrc'}\n")
+    cli = ["--Modelfile", cd.paths["model"], "--Particlesfile", str(tmp_path / "list.txt"), "--Inputfile", cd.paths["param"],
+           "--ReadOrientation", cd.paths["orient"], "--ReadMRC", "--ReadMultipleMRC", "--DumpMaps"]
+    ref_dir, our_dir, hook = tmp_path / "ref", tmp_path / "ours", tmp_path / "hook"
+    for d in (ref_dir, our_dir, hook):
+        d.mkdir()
+    r = subprocess.run([REF_BIN] + cli, cwd=ref_dir, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-400:] + r.stderr[-400:]
+    r = subprocess.run([exe] + cli, cwd=our_dir, capture_output=True, text=True,
+                       env={**os.environ, "BIOEM_B200_DUMP_INPUTS": str(hook)})
+    assert r.returncode == 0, r.stdout[-400:] + r.stderr[-400:]
+    a, b = (open(d / "maps.dump", "rb").read() for d in (ref_dir, our_dir))
+    assert len(a) == len(b) and a[:4] == b[:4] and np.frombuffer(a[:4], "<i4")[0] == len(imgs)
+    ma, mb = (np.frombuffer(x[4:], "<f4") for x in (a, b))
+    np.testing.assert_allclose(mb, ma, rtol=0, atol=2.5e-7 * np.abs(ma).max())  # -ffast-math rounding of the reference
+    # and the single-stack reading of the same images gives the same particles
+    single = tmp_path / "single"
+    single.mkdir()
+    from bioem_b200.cases import reference_cli
+    r = subprocess.run([exe] + reference_cli(cd) + ["--DumpMaps"], cwd=single, capture_output=True, text=True,
+                       env={**os.environ, "BIOEM_B200_DUMP_INPUTS": str(single)})
+    assert r.returncode == 0
+    assert open(single / "maps.dump", "rb").read() == b
