@@ -336,3 +336,39 @@ def test_multiple_mrc_list_matches_the_reference_binary(tmp_path):
                        env={**os.environ, "BIOEM_B200_DUMP_INPUTS": str(single)})
     assert r.returncode == 0
     assert open(single / "maps.dump", "rb").read() == b
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="reference binary not built (oracle/_ref)")
+def test_pdb_reader_matches_the_reference_binary(tmp_path):
+    """--ReadPDB (model.cpp:85-329,738-844): C-alpha atoms only, residue name -> radius / number of electrons
+    for all 20 residue types, fixed columns; the reference's model.dump is the witness."""
+    import subprocess
+    exe = _build_host_bin()
+    cd = build_case("toy32", str(tmp_path))
+    res = ["GLY", "ALA", "VAL", "LEU", "ILE", "MET", "PHE", "TRP", "PRO", "SER", "THR", "CYS", "TYR", "ASN", "GLN",
+           "ASP", "GLU", "LYS", "ARG", "HIS"]
+    rng = np.random.default_rng(5)
+    lines, serial = [], 1
+    for i, rn in enumerate(res):
+        for atom in ("N", "CA", "C"):
+            x, y, z = rng.uniform(-9.0, 9.0, size=3)
+            lines.append(f"ATOM  {serial:5d}  {atom:<3s} {rn} A{i + 1:4d}    {x:8.3f}{y:8.3f}{z:8.3f}  1.00  0.00")
+            serial += 1
+    lines += ["TER", "END"]
+    (tmp_path / "m.pdb").write_text("\n".join(lines) + "\n")
+    cli = ["--Modelfile", str(tmp_path / "m.pdb"), "--ReadPDB", "--Particlesfile", cd.paths["particles"], "--Inputfile",
+           cd.paths["param"], "--ReadOrientation", cd.paths["orient"], "--DumpModel"]
+    ref_dir, our_dir, hook = tmp_path / "ref", tmp_path / "ours", tmp_path / "hook"
+    for d in (ref_dir, our_dir, hook):
+        d.mkdir()
+    r = subprocess.run([REF_BIN] + cli, cwd=ref_dir, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-400:] + r.stderr[-400:]
+    r = subprocess.run([exe] + cli, cwd=our_dir, capture_output=True, text=True,
+                       env={**os.environ, "BIOEM_B200_DUMP_INPUTS": str(hook)})
+    assert r.returncode == 0, r.stdout[-400:] + r.stderr[-400:]
+    a, b = (open(d / "model.dump", "rb").read() for d in (ref_dir, our_dir))
+    assert len(a) == len(b) and a[4:8] == b[4:8] and np.frombuffer(a[4:8], "<i4")[0] == len(res)
+    assert abs(np.frombuffer(a[:4], "<f4")[0] - np.frombuffer(b[:4], "<f4")[0]) <= 4e-7 * np.frombuffer(a[:4], "<f4")[0]
+    pa, pb = (np.frombuffer(x[8:], "<f4").reshape(-1, 6) for x in (a, b))
+    for col in (0, 1, 2, 4, 5):
+        assert pa[:, col].tobytes() == pb[:, col].tobytes(), col
