@@ -372,3 +372,39 @@ def test_pdb_reader_matches_the_reference_binary(tmp_path):
     pa, pb = (np.frombuffer(x[8:], "<f4").reshape(-1, 6) for x in (a, b))
     for col in (0, 1, 2, 4, 5):
         assert pa[:, col].tobytes() == pb[:, col].tobytes(), col
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="reference binary not built (oracle/_ref)")
+def test_mrc_volume_model_reader_matches_the_reference_binary(tmp_path):
+    """--ReadModelMRC (model.cpp:332-416, BASELINE configs[3]): one model point per voxel of a mode-2 volume at
+    ((i - nx/2) px, (j - ny/2) px, (k - nz/2) px), radius 2 px, density = voxel; witness: the reference's model.dump."""
+    import struct
+    import subprocess
+    exe = _build_host_bin()
+    cd = build_case("toy32", str(tmp_path))
+    nx, ny, nz = 6, 5, 4
+    vol = np.random.default_rng(2).uniform(0.0, 3.0, size=(nz, ny, nx)).astype("<f4")  # file order: x fastest
+    hdr = bytearray(1024)
+    struct.pack_into("<4i", hdr, 0, nx, ny, nz, 2)
+    struct.pack_into("<3i", hdr, 28, nx, ny, nz)
+    struct.pack_into("<3f", hdr, 40, float(nx), float(ny), float(nz))
+    struct.pack_into("<3f", hdr, 52, 90.0, 90.0, 90.0)
+    struct.pack_into("<3i", hdr, 64, 1, 2, 3)
+    hdr[208:212] = b"MAP "
+    (tmp_path / "model.mrc").write_bytes(bytes(hdr) + vol.tobytes())
+    cli = ["--Modelfile", str(tmp_path / "model.mrc"), "--ReadModelMRC", "--Particlesfile", cd.paths["particles"],
+           "--Inputfile", cd.paths["param"], "--ReadOrientation", cd.paths["orient"], "--DumpModel"]
+    ref_dir, our_dir, hook = tmp_path / "ref", tmp_path / "ours", tmp_path / "hook"
+    for d in (ref_dir, our_dir, hook):
+        d.mkdir()
+    r = subprocess.run([REF_BIN] + cli, cwd=ref_dir, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-400:] + r.stderr[-400:]
+    r = subprocess.run([exe] + cli, cwd=our_dir, capture_output=True, text=True,
+                       env={**os.environ, "BIOEM_B200_DUMP_INPUTS": str(hook)})
+    assert r.returncode == 0, r.stdout[-400:] + r.stderr[-400:]
+    a, b = (open(d / "model.dump", "rb").read() for d in (ref_dir, our_dir))
+    assert len(a) == len(b) and a[4:8] == b[4:8] and np.frombuffer(a[4:8], "<i4")[0] == nx * ny * nz
+    assert abs(np.frombuffer(a[:4], "<f4")[0] - np.frombuffer(b[:4], "<f4")[0]) <= 4e-7 * np.frombuffer(a[:4], "<f4")[0]
+    pa, pb = (np.frombuffer(x[8:], "<f4").reshape(-1, 6) for x in (a, b))
+    for col in (0, 1, 2, 4, 5):
+        assert pa[:, col].tobytes() == pb[:, col].tobytes(), col
