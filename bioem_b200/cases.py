@@ -36,6 +36,7 @@ class Case:
     particle_format: str = "text"   # "text" | "mrc"
     extra: tuple = ()               # further parameter-file lines (optional keywords)
     angle_priors: bool = False      # PRIOR_ANGLES: a fifth column (log prior) in the orientation list
+    euler_grid: tuple = ()          # (GRIDPOINTS_ALPHA, GRIDPOINTS_BETA): Euler-angle grid instead of a quaternion list
 
     @property
     def use_psf(self) -> bool:
@@ -67,6 +68,9 @@ CASES = {
                                               "ELECTRON_WAVELENGTH 0.0251", "SIGMA_PRIOR_AMP_CTF 0.3",
                                               "PRIOR_AMP_CTF_CENTER 0.1", "SIGMA_PRIOR_DEFOCUS 1.5"),
                       angle_priors=True),
+    # Euler-angle grid generated from the parameter file (ZXZ rotation path, alpha/beta/gamma output header)
+    "toy32euler": Case("toy32euler", 32, 1.5, 60, 3, 576, 16, CFG1_CTF, 4, 1, write_angles=3, model_sigma=5.0,
+                       model_rmax=12.0, euler_grid=(4, 3)),
     "toy36g2": Case("toy36g2", 36, 1.5, 60, 4, 576, 16, CFG1_CTF, 6, 2, model_sigma=6.0,
                     model_rmax=14.0, particle_format="mrc"),
     "toy64": Case("toy64", 64, 1.5, 200, 5, 576, 32, synth.PRODUCTION_GRID, 10, 1,
@@ -122,9 +126,10 @@ def build_case(name_or_case, outdir: str | None = None, n_particles: int | None 
                                             else "particles.txt"))
         synth.write_model_text(paths["model"], model)
         extra = list(c.extra) + (["USE_PSF", "WRITE_CTF_PARAM 1"] if c.use_psf else []) + \
-            (["PRIOR_ANGLES"] if c.angle_priors else [])
+            (["PRIOR_ANGLES"] if c.angle_priors else []) + \
+            ([f"GRIDPOINTS_ALPHA {c.euler_grid[0]}", f"GRIDPOINTS_BETA {c.euler_grid[1]}"] if c.euler_grid else [])
         synth.write_param_file(paths["param"], c.n_pixels, c.pixel_size, c.max_disp, c.grid_space,
-                               c.ctf, True, c.write_angles, extra=extra or None)
+                               c.ctf, not c.euler_grid, c.write_angles, extra=extra or None)
         if c.angle_priors:  # log priors -0.5, -0.25, 0, ... per orientation (exact in the 12-column format)
             pri = (-0.5 + 0.25 * (np.arange(len(quats)) % 5)).astype(np.float32)
             synth.write_orientation_list(paths["orient"], np.concatenate([quats, pri[:, None]], axis=1))
@@ -141,8 +146,9 @@ def reference_cli(cd: CaseData, outfile: str = "Output_Probabilities") -> list[s
     """Command-line arguments (after the binary name) in the reference's CLI
     (bioem.cpp:193-224) for a built case."""
     a = ["--Modelfile", cd.paths["model"], "--Particlesfile", cd.paths["particles"],
-         "--Inputfile", cd.paths["param"], "--ReadOrientation", cd.paths["orient"],
-         "--OutputFile", outfile]
+         "--Inputfile", cd.paths["param"], "--OutputFile", outfile]
+    if not cd.case.euler_grid:
+        a += ["--ReadOrientation", cd.paths["orient"]]
     if cd.case.particle_format == "mrc":
         a.append("--ReadMRC")
     return a

@@ -30,7 +30,7 @@ def _run(name, tmp_path, env=None):
     return cd
 
 
-@pytest.mark.parametrize("name", ["toy32", "toy32psf", "toy32opts", "toy64", "cfg1", "cfg2_slice"])
+@pytest.mark.parametrize("name", ["toy32", "toy32psf", "toy32opts", "toy32euler", "toy64", "cfg1", "cfg2_slice"])
 def test_binary_output_probabilities_match_reference_golden(name, tmp_path, golden_dir):
     cd = _run(name, tmp_path)
     got_path = tmp_path / "Output_Probabilities"
@@ -48,7 +48,8 @@ def test_binary_output_probabilities_match_reference_golden(name, tmp_path, gold
         for a, b in zip(gt, rt):
             if not _is_number(b):
                 assert a == b, (g, r)
-    got, ref = parse_output_probabilities(str(got_path)), parse_output_probabilities(ref_path)
+    quat = not cd.case.euler_grid  # Euler grids print alpha / beta / gamma (three angle columns)
+    got, ref = parse_output_probabilities(str(got_path), quat), parse_output_probabilities(ref_path, quat)
     n = cd.case.n_pixels
     same = 0
     for m in range(len(ref["logp"])):
@@ -72,7 +73,7 @@ def _is_number(tok):
         return False
 
 
-@pytest.mark.parametrize("name", ["toy32", "toy32opts"])
+@pytest.mark.parametrize("name", ["toy32", "toy32opts", "toy32euler"])
 def test_binary_ang_prob_matches_reference_golden(name, tmp_path, golden_dir):
     """WRITE_PROB_ANGLES: same header, same number of rows per image, same top orientation and
     log-probabilities within tolerance (the order further down the list may swap on near-ties).
@@ -84,16 +85,19 @@ def test_binary_ang_prob_matches_reference_golden(name, tmp_path, golden_dir):
     g = np.array([[float(x) for x in ln.replace("Separated:", "").split()] for ln in got[3:] if ln.strip()])
     r = np.array([[float(x) for x in ln.replace("Separated:", "").split()] for ln in ref[3:] if ln.strip()])
     assert g.shape == r.shape
+    na = 3 if name == "toy32euler" else 4  # angle columns: alpha beta gamma, or q1..q4
+    lp = 1 + na                              # then logP, three "Separated:" terms and, with PRIOR_ANGLES, the prior
     for m in np.unique(r[:, 0]):
         gm, rm = g[g[:, 0] == m], r[r[:, 0] == m]
-        key = gm[:, 5] - (gm[:, 9] if gm.shape[1] > 9 else 0.0)
+        has_prior = gm.shape[1] > lp + 4
+        key = gm[:, lp] - (gm[:, lp + 4] if has_prior else 0.0)
         assert np.all(np.diff(key) <= 1e-3)  # descending log-probability (before the angle prior, 4 decimals)
-        if gm.shape[1] > 9:
-            np.testing.assert_array_equal(gm[:, 9], rm[:, 9])
-        np.testing.assert_allclose(gm[:, 5], rm[:, 5], atol=5e-3 + 1e-4)
+        if has_prior:
+            np.testing.assert_array_equal(gm[:, lp + 4], rm[:, lp + 4])
+        np.testing.assert_allclose(gm[:, lp], rm[:, lp], atol=5e-3 + 1e-4)
         # same set of orientations up to swaps between near-equal entries
-        gs = {tuple(np.round(x, 3)) for x in gm[:, 1:5]}
-        rs = {tuple(np.round(x, 3)) for x in rm[:, 1:5]}
+        gs = {tuple(np.round(x, 3)) for x in gm[:, 1:lp]}
+        rs = {tuple(np.round(x, 3)) for x in rm[:, 1:lp]}
         assert len(gs & rs) >= len(rs) - 1
 
 
