@@ -37,6 +37,7 @@ class Case:
     extra: tuple = ()               # further parameter-file lines (optional keywords)
     angle_priors: bool = False      # PRIOR_ANGLES: a fifth column (log prior) in the orientation list
     euler_grid: tuple = ()          # (GRIDPOINTS_ALPHA, GRIDPOINTS_BETA): Euler-angle grid instead of a quaternion list
+    small_radii: bool = False       # every second model point gets a radius below the pixel size (point branch)
 
     @property
     def use_psf(self) -> bool:
@@ -71,6 +72,10 @@ CASES = {
     # Euler-angle grid generated from the parameter file (ZXZ rotation path, alpha/beta/gamma output header)
     "toy32euler": Case("toy32euler", 32, 1.5, 60, 3, 576, 16, CFG1_CTF, 4, 1, write_angles=3, model_sigma=5.0,
                        model_rmax=12.0, euler_grid=(4, 3)),
+    # both rasterisation branches of createProjection: radius <= pixel size adds the density to one pixel
+    # (bioem.cpp:1719-1739), larger radii the sphere footprint (:1745-1801)
+    "toy32pts": Case("toy32pts", 32, 1.5, 60, 3, 576, 16, CFG1_CTF, 4, 1, model_sigma=5.0, model_rmax=12.0,
+                     small_radii=True),
     "toy36g2": Case("toy36g2", 36, 1.5, 60, 4, 576, 16, CFG1_CTF, 6, 2, model_sigma=6.0,
                     model_rmax=14.0, particle_format="mrc"),
     "toy64": Case("toy64", 64, 1.5, 200, 5, 576, 32, synth.PRODUCTION_GRID, 10, 1,
@@ -109,6 +114,8 @@ def build_case(name_or_case, outdir: str | None = None, n_particles: int | None 
         c = Case(**{**c.__dict__, "n_particles": n_particles or c.n_particles,
                     "n_orient": n_orient or c.n_orient})
     model = synth.make_model(c.n_atoms, seed=1, sigma=c.model_sigma, rmax=c.model_rmax)
+    if c.small_radii:
+        model[::2, 3] = np.round(model[::2, 3] * 0.3, 4)
     quats = synth.load_quaternions(c.quat_list)[:c.n_orient].copy()
     ctfp = synth.ctf_grid_params(CFG1_CTF if c.use_psf else c.ctf)
     imgs, truth = synth.make_particles(model, quats, c.n_pixels, c.pixel_size, c.n_particles,
