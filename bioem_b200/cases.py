@@ -76,6 +76,10 @@ CASES = {
     # (bioem.cpp:1719-1739), larger radii the sphere footprint (:1745-1801)
     "toy32pts": Case("toy32pts", 32, 1.5, 60, 3, 576, 16, CFG1_CTF, 4, 1, model_sigma=5.0, model_rmax=12.0,
                      small_radii=True),
+    # a model wider than the frame: points whose pixel (or sphere footprint) leaves the image are skipped with
+    # a warning, in both rasterisation branches (bioem.cpp:1724-1734,1756-1780)
+    "toy32clip": Case("toy32clip", 32, 1.5, 60, 3, 576, 16, CFG1_CTF, 4, 1, model_sigma=13.0, model_rmax=30.0,
+                      small_radii=True),
     "toy36g2": Case("toy36g2", 36, 1.5, 60, 4, 576, 16, CFG1_CTF, 6, 2, model_sigma=6.0,
                     model_rmax=14.0, particle_format="mrc"),
     "toy64": Case("toy64", 64, 1.5, 200, 5, 576, 32, synth.PRODUCTION_GRID, 10, 1,

@@ -51,7 +51,7 @@ def setups():
         v[3].close()
 
 
-@pytest.mark.parametrize("name", ["toy32", "toy32pts", "toy36g2", "toy64", "cfg1", "cfg2_slice", "cfg4_slice"])
+@pytest.mark.parametrize("name", ["toy32", "toy32pts", "toy32clip", "toy36g2", "toy64", "cfg1", "cfg2_slice", "cfg4_slice"])
 def test_stage1_projection_matches_oracle(setups, name):
     cd, hi, parts, eng, P = setups(name)
     for o in (0, P.O - 1):
