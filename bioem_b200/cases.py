@@ -80,6 +80,10 @@ CASES = {
     # a warning, in both rasterisation branches (bioem.cpp:1724-1734,1756-1780)
     "toy32clip": Case("toy32clip", 32, 1.5, 60, 3, 576, 16, CFG1_CTF, 4, 1, model_sigma=13.0, model_rmax=30.0,
                       small_radii=True),
+    # all three CTF grid axes longer than one: pins the enumeration order amplitude / defocus / envelope
+    "toy32amp": Case("toy32amp", 32, 1.5, 60, 3, 576, 12, dict(CTF_DEFOCUS=(1.0, 4.0, 3), CTF_B_ENV=(2.0, 300.0, 2),
+                                                                CTF_AMPLITUDE=(0.05, 0.25, 2)), 4, 1,
+                     model_sigma=5.0, model_rmax=12.0),
     "toy36g2": Case("toy36g2", 36, 1.5, 60, 4, 576, 16, CFG1_CTF, 6, 2, model_sigma=6.0,
                     model_rmax=14.0, particle_format="mrc"),
     "toy64": Case("toy64", 64, 1.5, 200, 5, 576, 32, synth.PRODUCTION_GRID, 10, 1,

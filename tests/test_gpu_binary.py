@@ -30,7 +30,7 @@ def _run(name, tmp_path, env=None):
     return cd
 
 
-@pytest.mark.parametrize("name", ["toy32", "toy32psf", "toy32opts", "toy32euler", "toy32pts", "toy32clip", "toy64", "cfg1", "cfg2_slice"])
+@pytest.mark.parametrize("name", ["toy32", "toy32psf", "toy32opts", "toy32euler", "toy32pts", "toy32clip", "toy32amp", "toy64", "cfg1", "cfg2_slice"])
 def test_binary_output_probabilities_match_reference_golden(name, tmp_path, golden_dir):
     cd = _run(name, tmp_path)
     got_path = tmp_path / "Output_Probabilities"

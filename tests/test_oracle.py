@@ -75,7 +75,7 @@ def _check_against_reference_output(P, res, ref, n):
     return near_ties
 
 
-@pytest.mark.parametrize("name", ["toy32", "toy32psf", "toy32d0", "toy32full", "toy32pts", "toy32clip", "toy36g2", "toy64", "cfg1", "cfg2_slice",
+@pytest.mark.parametrize("name", ["toy32", "toy32psf", "toy32d0", "toy32full", "toy32pts", "toy32clip", "toy32amp", "toy36g2", "toy64", "cfg1", "cfg2_slice",
                                   "cfg5_slice"])
 def test_oracle_matches_reference_golden(name, golden_dir):
     cd, P, res = _run_oracle(name)
