@@ -667,7 +667,7 @@ void read_model(const Options &o, const Params &p, std::vector<bioem_b200_model_
         for (int k = 0; k < 3; k++)
           pt.pos[k] -= cm[k];
     }
-    std::cout << "Total Number of Voxels " << pts.size() << "\nEffective number of electrons " << NormDen << "\n";
+    std::cout << "Total Number of Voxels " << pts.size() << "\nTotal Number of Electrons " << NormDen << "\n+++++++++++++++++++++++++++++++++++++++++ \n";
     if (o.printCoordRead)
       print_coordread(pts);
     return;
@@ -800,7 +800,7 @@ void read_model(const Options &o, const Params &p, std::vector<bioem_b200_model_
     fclose(f);
   }
   NormDen = bioem_b200_host_model_prepare(pts.data(), (int) pts.size(), p.nocentermass ? 0 : 1);
-  std::cout << "Total Number of Voxels " << pts.size() << "\nEffective number of electrons " << NormDen << "\n";
+  std::cout << "Total Number of Voxels " << pts.size() << "\nTotal Number of Electrons " << NormDen << "\n+++++++++++++++++++++++++++++++++++++++++ \n";
   if (o.printCoordRead)
     print_coordread(pts);
 }
