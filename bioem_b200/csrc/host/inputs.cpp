@@ -228,6 +228,7 @@ void read_parameters(const std::string &file, Params &p)
       p.angleGridPointsAlpha = n(1);
       if (p.angleGridPointsAlpha < 0)
         fail("Negative GRIDPOINTS_ALPHA");
+      std::cout << "Grid points alpha " << p.angleGridPointsAlpha << "\n";
       yAl = true;
     }
     else if (k == "GRIDPOINTS_BETA")
@@ -235,6 +236,7 @@ void read_parameters(const std::string &file, Params &p)
       p.angleGridPointsBeta = n(1);
       if (p.angleGridPointsBeta < 0)
         fail("Negative GRIDPOINTS_BETA");
+      std::cout << "Grid points in Cosine ( beta ) " << p.angleGridPointsBeta << "\n";
       yBe = true;
     }
     else if (k == "USE_QUATERNIONS")
@@ -253,11 +255,13 @@ void read_parameters(const std::string &file, Params &p)
     else if (k == "CTF_B_ENV")
     {
       grid3(startB, endB, p.nEnv, "B Env.");
+      std::cout << "Grid CTF B-ENV: " << startB << " " << endB << " " << p.nEnv << "\n";
       yB = true;
     }
     else if (k == "CTF_DEFOCUS")
     {
       grid3(startDef, endDef, p.nPhase, "defocus");
+      std::cout << "Grid CTF Defocus: " << startDef << " " << endDef << " " << p.nPhase << "\n";
       if (endDef > 8.)
         fail("Defocus beyond 8micro-m range is not allowed");
       yDef = true;
@@ -265,6 +269,7 @@ void read_parameters(const std::string &file, Params &p)
     else if (k == "CTF_AMPLITUDE" || k == "PSF_AMPLITUDE")
     {
       grid3(p.startAmp, p.endAmp, p.nAmp, "amplitude");
+      std::cout << "Grid Amplitude: " << p.startAmp << " " << p.endAmp << " " << p.nAmp << "\n";
       yAmp = true;
     }
     else if (k == "ELECTRON_WAVELENGTH")
@@ -281,11 +286,13 @@ void read_parameters(const std::string &file, Params &p)
     else if (k == "PSF_ENVELOPE")
     {
       grid3(p.startEnv, p.endEnv, p.nEnv, "PSF Env.");
+      std::cout << "Grid PSF Envelope: " << p.startEnv << " " << p.endEnv << " " << p.nEnv << "\n";
       yPenv = true;
     }
     else if (k == "PSF_PHASE")
     {
       grid3(p.startPhase, p.endPhase, p.nPhase, "PSF phase");
+      std::cout << "Grid PSF phase: " << p.startPhase << " " << p.endPhase << " " << p.nPhase << "\n";
       yPpha = true;
     }
     else if (k == "DISPLACE_CENTER")
@@ -293,9 +300,11 @@ void read_parameters(const std::string &file, Params &p)
       p.maxDisplaceCenter = n(1);
       if (p.maxDisplaceCenter < 0)
         fail("Negative MAX_D_CENTER");
+      std::cout << "Maximum displacement Center " << p.maxDisplaceCenter << "\n";
       p.GridSpaceCenter = n(2);
       if (p.GridSpaceCenter < 0)
         fail("Negative PIXEL_GRID_CENTER");
+      std::cout << "Grid space displacement center " << p.GridSpaceCenter << "\n";
       yMDC = true;
     }
     else if (k == "WRITE_PROB_ANGLES")
@@ -303,6 +312,7 @@ void read_parameters(const std::string &file, Params &p)
       p.writeAngles = n(1);
       if (p.writeAngles < 0)
         fail("Negative WRITE_PROB_ANGLES");
+      std::cout << "Writing " << p.writeAngles << " Probabilies of each angle \n";
     }
     else if (k == "IGNORE_PDB")
       p.ignorePDB = true;
@@ -338,6 +348,8 @@ void read_parameters(const std::string &file, Params &p)
       p.Priorampcent = f(1);
     // unknown keywords are skipped silently, like the reference
   }
+  std::cout << "To verify input of Priors:\nSigma Prior B-Env: " << p.sigmaPriorbctf << "\nSigma Prior Defocus: " << p.sigmaPriordefo
+            << "\nCenter Prior Defocus: " << p.Priordefcent << "\n";
   if (!yPix)
     fail("Input missing: please provide PIXEL_SIZE");
   if (!yNum)
