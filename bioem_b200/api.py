@@ -52,7 +52,10 @@ EXPORTS = [
     "bioem_b200_reset",
     "bioem_b200_run", "bioem_b200_synchronize", "bioem_b200_download", "bioem_b200_download_top_angles",
     "bioem_b200_partial_bytes", "bioem_b200_export_partial", "bioem_b200_import_partials",
-    "bioem_b200_merge_host", "bioem_b200_stream", "bioem_b200_device_angles", "bioem_b200_stats",
+    "bioem_b200_merge_host", "bioem_b200_merge_peers", "bioem_b200_merge_top_angles_peers",
+    "bioem_b200_nccl_unique_id", "bioem_b200_nccl_init", "bioem_b200_nccl_attach", "bioem_b200_merge_nccl",
+    "bioem_b200_top_angles_nccl", "bioem_b200_set_kernel_timing", "bioem_b200_out_of_frame",
+    "bioem_b200_exact_argmax_info", "bioem_b200_stream", "bioem_b200_device_angles", "bioem_b200_stats",
     "bioem_b200_kernel_time", "bioem_b200_debug_projection", "bioem_b200_debug_convolved",
     "bioem_b200_debug_correlation", "bioem_b200_debug_particle",
     "bioem_b200_host_defocus_to_phase", "bioem_b200_host_ctf_table", "bioem_b200_host_psf_kernels",
@@ -102,6 +105,17 @@ def lib():
     L.bioem_b200_export_partial.argtypes = [vp, vp]
     L.bioem_b200_import_partials.argtypes = [vp, vp, C.c_int]
     L.bioem_b200_merge_host.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.bioem_b200_merge_peers.argtypes = [C.POINTER(vp), C.c_int]
+    L.bioem_b200_merge_top_angles_peers.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int,
+                                                    C.c_int, vp]
+    L.bioem_b200_nccl_unique_id.argtypes = [vp]
+    L.bioem_b200_nccl_init.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.bioem_b200_nccl_attach.argtypes = [vp, vp]
+    L.bioem_b200_merge_nccl.argtypes = [vp]
+    L.bioem_b200_top_angles_nccl.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp]
+    L.bioem_b200_set_kernel_timing.argtypes = [vp, C.c_int]
+    L.bioem_b200_out_of_frame.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_longlong)]
+    L.bioem_b200_exact_argmax_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.bioem_b200_stream.argtypes = [vp]
     L.bioem_b200_stream.restype = vp
     L.bioem_b200_device_angles.argtypes = [vp]
@@ -306,10 +320,12 @@ class Engine:
     def synchronize(self):
         _chk(lib().bioem_b200_synchronize(self._h), "synchronize")
 
-    def download(self, out_maps: np.ndarray | None = None, out_angles: np.ndarray | None = None):
+    def download(self, out_maps: np.ndarray | None = None, out_angles=None):
+        """(maps[M], angle table [O, M] or None).  out_angles=False skips the O x M x 16-byte angle table
+        (WRITE_PROB_ANGLES runs that only need the top-K rows, download_top_angles)."""
         pm = out_maps if out_maps is not None else np.zeros(self.M, dtype=PROB_MAP_DTYPE)
-        pa = out_angles
-        if pa is None and self.cfg.writeAngles:
+        pa = None if out_angles is False else out_angles
+        if pa is None and out_angles is not False and self.cfg.writeAngles:
             pa = np.zeros((self.O, self.M), dtype=PROB_ANGLE_DTYPE)
         _chk(lib().bioem_b200_download(self._h, pm.ctypes.data, pa.ctypes.data if pa is not None else None),
              "download")
@@ -333,6 +349,22 @@ class Engine:
     def import_partials(self, device_ptr: int, n_ranks: int):
         _chk(lib().bioem_b200_import_partials(self._h, C.c_void_p(device_ptr), int(n_ranks)), "import_partials")
 
+    def nccl_init(self, n_ranks: int, rank: int, unique_id: bytes):
+        """Build this handle's NCCL communicator from the 128-byte id rank 0 made with nccl_unique_id()
+        (the launcher broadcasts it: plumbing)."""
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        _chk(lib().bioem_b200_nccl_init(self._h, int(n_ranks), int(rank), buf), "nccl_init")
+
+    def merge_nccl(self):
+        """One NCCL all-gather of the per-image partials + the fold in rank order, on the handle's stream."""
+        _chk(lib().bioem_b200_merge_nccl(self._h), "merge_nccl")
+
+    def top_angles_nccl(self, k: int, o_begin: int, o_end: int) -> np.ndarray:
+        out = np.zeros((self.M, k), dtype=TOP_ANGLE_DTYPE)
+        _chk(lib().bioem_b200_top_angles_nccl(self._h, int(o_begin), int(o_end), int(k), out.ctypes.data),
+             "top_angles_nccl")
+        return out
+
     def device_angles(self) -> int:
         return int(lib().bioem_b200_device_angles(self._h) or 0)
 
@@ -341,6 +373,23 @@ class Engine:
         a, b = C.c_longlong(), C.c_longlong()
         _chk(lib().bioem_b200_stats(self._h, C.byref(a), C.byref(b)), "stats")
         return a.value, b.value
+
+    def set_kernel_timing(self, on: bool = True):
+        _chk(lib().bioem_b200_set_kernel_timing(self._h, int(on)), "set_kernel_timing")
+
+    def out_of_frame(self):
+        """(per-orientation counts [O], total) of model points skipped because they left the frame."""
+        per = np.zeros(self.O, dtype=np.int32)
+        tot = C.c_longlong()
+        _chk(lib().bioem_b200_out_of_frame(self._h, per.ctypes.data_as(C.POINTER(C.c_int)), C.byref(tot)),
+             "out_of_frame")
+        return per, tot.value
+
+    def exact_argmax_info(self):
+        """(re-evaluated, corrected, disagreed) of the exact arg-max pass of the last download()."""
+        a, b, c = C.c_int(), C.c_int(), C.c_int()
+        _chk(lib().bioem_b200_exact_argmax_info(self._h, C.byref(a), C.byref(b), C.byref(c)), "exact_argmax_info")
+        return a.value, b.value, c.value
 
     def kernel_time(self):
         t, n = C.c_double(), C.c_longlong()
@@ -363,8 +412,8 @@ class Engine:
         return out, s.value, ss.value
 
     def debug_correlation(self, o: int, c: int, m: int) -> np.ndarray:
-        npos = self.cfg.maxDisplaceCenter // self.cfg.GridSpaceCenter + 1
-        nw = 2 * npos - 1
+        d, g = self.cfg.maxDisplaceCenter, self.cfg.GridSpaceCenter
+        nw = d // g + 1 + (d + g - 1) // g  # Algo 1's window (bioem_algorithm.h:156-197), quirk Q3
         out = np.zeros(nw * nw, dtype=np.float32)
         nv = C.c_int()
         _chk(lib().bioem_b200_debug_correlation(self._h, int(o), int(c), int(m), _fp(out), C.byref(nv)),
@@ -384,6 +433,28 @@ def merge_host(parts: np.ndarray) -> np.ndarray:
     p = np.ascontiguousarray(parts)
     out = np.zeros(p.shape[1], dtype=PROB_MAP_DTYPE)
     _chk(lib().bioem_b200_merge_host(p.ctypes.data, p.shape[0], p.shape[1], out.ctypes.data), "merge_host")
+    return out
+
+
+def nccl_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    _chk(lib().bioem_b200_nccl_unique_id(buf), "nccl_unique_id")
+    return buf.raw
+
+
+def merge_peers(engines) -> None:
+    """Single process, one Engine per GPU (or several on one GPU): merged state lands in engines[0]."""
+    arr = (C.c_void_p * len(engines))(*[e._h for e in engines])
+    _chk(lib().bioem_b200_merge_peers(arr, len(engines)), "merge_peers")
+
+
+def merge_top_angles_peers(engines, blocks, k: int) -> np.ndarray:
+    arr = (C.c_void_p * len(engines))(*[e._h for e in engines])
+    ob = (C.c_int * len(engines))(*[int(b[0]) for b in blocks])
+    oe = (C.c_int * len(engines))(*[int(b[1]) for b in blocks])
+    out = np.zeros((engines[0].M, k), dtype=TOP_ANGLE_DTYPE)
+    _chk(lib().bioem_b200_merge_top_angles_peers(arr, ob, oe, len(engines), int(k), out.ctypes.data),
+         "merge_top_angles_peers")
     return out
 
 

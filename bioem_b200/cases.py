@@ -38,6 +38,8 @@ class Case:
     angle_priors: bool = False      # PRIOR_ANGLES: a fifth column (log prior) in the orientation list
     euler_grid: tuple = ()          # (GRIDPOINTS_ALPHA, GRIDPOINTS_BETA): Euler-angle grid instead of a quaternion list
     small_radii: bool = False       # every second model point gets a radius below the pixel size (point branch)
+    voxel_model: int = 0            # edge of an MRC density volume read with --ReadModelMRC (0: text model)
+    bulk_particles: int = 0         # > 0: large stack made from that many distinct clean signals (throughput workloads)
 
     @property
     def use_psf(self) -> bool:
@@ -97,7 +99,20 @@ CASES = {
     "cfg2": Case("cfg2", 224, 1.0, 1000, 1000, 4608, 4608, synth.PRODUCTION_GRID, 40, 1,
                  particle_format="mrc"),
     "cfg3": Case("cfg3", 224, 1.0, 1000, 10000, 36864, 36864, synth.PRODUCTION_GRID, 40, 1,
-                 particle_format="mrc"),
+                 particle_format="mrc", bulk_particles=1000),
+    # DISPLACE_CENTER whose spacing does not divide the maximum displacement: Algo 1 enumerates 0,2,4 and
+    # N-5,N-3,N-1 (3 + 3 points per axis), not a symmetric set (quirk Q3, bioem_algorithm.h:156-197)
+    "toy32g2odd": Case("toy32g2odd", 32, 1.5, 60, 3, 576, 12, CFG1_CTF, 5, 2, model_sigma=5.0, model_rmax=12.0),
+    "toy32g3": Case("toy32g3", 32, 1.5, 60, 3, 576, 12, CFG1_CTF, 7, 3, write_angles=2, model_sigma=5.0, model_rmax=12.0),
+    # BASELINE.json configs[3] at its named shape: 48^3 MRC density volume (110,592 points of radius 2 px) read with
+    # --ReadModelMRC, 360 x 360 pixels, dense CTF grid 16 x 8 x 2 = 256; a slice of particles / orientations so
+    # that the unmodified reference finishes in seconds
+    "cfg4_voxel_slice": Case("cfg4_voxel_slice", 360, 2.0, 0, 3, 4608, 2, DENSE_CTF, 40, 1, particle_format="mrc",
+                             voxel_model=48),
+    "cfg4": Case("cfg4", 360, 2.0, 0, 2000, 4608, 4608, DENSE_CTF, 40, 1, particle_format="mrc", voxel_model=48,
+                 bulk_particles=64),
+    "cfg5": Case("cfg5", 224, 1.0, 1000, 5000, 4608, 4608, synth.PRODUCTION_GRID, 40, 1, write_angles=10,
+                 particle_format="mrc", bulk_particles=1000),
     "cfg4_slice": Case("cfg4_slice", 360, 2.0, 1000, 4, 4608, 4, DENSE_CTF, 40, 1,
                        model_sigma=40.0, model_rmax=110.0, particle_format="mrc"),
     "cfg5_slice": Case("cfg5_slice", 224, 1.0, 1000, 5, 4608, 12, synth.PRODUCTION_GRID, 40, 1,
@@ -121,25 +136,39 @@ def build_case(name_or_case, outdir: str | None = None, n_particles: int | None 
     if n_particles is not None or n_orient is not None:
         c = Case(**{**c.__dict__, "n_particles": n_particles or c.n_particles,
                     "n_orient": n_orient or c.n_orient})
-    model = synth.make_model(c.n_atoms, seed=1, sigma=c.model_sigma, rmax=c.model_rmax)
+    vol = None
+    if c.voxel_model:
+        vol = synth.make_volume(c.voxel_model, seed=2)
+        model = synth.volume_to_points(vol, c.pixel_size)
+    else:
+        model = synth.make_model(c.n_atoms, seed=1, sigma=c.model_sigma, rmax=c.model_rmax)
     if c.small_radii:
         model[::2, 3] = np.round(model[::2, 3] * 0.3, 4)
     quats = synth.load_quaternions(c.quat_list)[:c.n_orient].copy()
     ctfp = synth.ctf_grid_params(CFG1_CTF if c.use_psf else c.ctf)
-    imgs, truth = synth.make_particles(model, quats, c.n_pixels, c.pixel_size, c.n_particles,
-                                       c.max_disp, ctfp, snr=0.1, seed=100,
-                                       normalise=(c.particle_format == "mrc"))
+    if c.bulk_particles:
+        imgs, truth = synth.make_particles_bulk(model, quats, c.n_pixels, c.pixel_size, c.n_particles, c.max_disp, ctfp,
+                                                n_distinct=c.bulk_particles, snr=0.1, seed=100,
+                                                normalise=(c.particle_format == "mrc"))
+    else:
+        imgs, truth = synth.make_particles(model, quats, c.n_pixels, c.pixel_size, c.n_particles,
+                                           c.max_disp, ctfp, snr=0.1, seed=100,
+                                           normalise=(c.particle_format == "mrc"))
     if c.particle_format == "text":
         # the text format carries 8 decimals: make array == file
         imgs = np.round(imgs.astype(np.float64), 8).astype(np.float32)
     paths = {}
     if outdir is not None:
         os.makedirs(outdir, exist_ok=True)
-        paths = dict(model=os.path.join(outdir, "model.txt"), param=os.path.join(outdir, "param.txt"),
+        paths = dict(model=os.path.join(outdir, "model.mrc" if c.voxel_model else "model.txt"),
+                     param=os.path.join(outdir, "param.txt"),
                      orient=os.path.join(outdir, "orient.txt"),
                      particles=os.path.join(outdir, "particles.mrc" if c.particle_format == "mrc"
                                             else "particles.txt"))
-        synth.write_model_text(paths["model"], model)
+        if c.voxel_model:
+            synth.write_volume_mrc(paths["model"], vol)
+        else:
+            synth.write_model_text(paths["model"], model)
         extra = list(c.extra) + (["USE_PSF", "WRITE_CTF_PARAM 1"] if c.use_psf else []) + \
             (["PRIOR_ANGLES"] if c.angle_priors else []) + \
             ([f"GRIDPOINTS_ALPHA {c.euler_grid[0]}", f"GRIDPOINTS_BETA {c.euler_grid[1]}"] if c.euler_grid else [])
@@ -166,4 +195,6 @@ def reference_cli(cd: CaseData, outfile: str = "Output_Probabilities") -> list[s
         a += ["--ReadOrientation", cd.paths["orient"]]
     if cd.case.particle_format == "mrc":
         a.append("--ReadMRC")
+    if cd.case.voxel_model:
+        a.append("--ReadModelMRC")
     return a

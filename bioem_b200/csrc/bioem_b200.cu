@@ -28,6 +28,59 @@ static int fail(int code, const std::string &msg)
       return fail(BIOEM_B200_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));               \
   } while (0)
 
+// ---------------------------------------------------------------------------------
+// NCCL is bound at run time (dlopen of libnccl.so.2: inside a PyTorch process that is the library torch
+// has already loaded; for the stand-alone binary the system one), so the library itself has no link-time
+// dependency on it and loads on boxes without NCCL.  Only the prototypes come from <nccl.h>.
+// ---------------------------------------------------------------------------------
+#include <dlfcn.h>
+#include <nccl.h>
+struct NcclApi
+{
+  void *lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*CommCount)(const ncclComm_t, int *) = nullptr;
+  ncclResult_t (*CommUserRank)(const ncclComm_t, int *) = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi *nccl_api()
+{
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried)
+  {
+    tried = true;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *nme : names)
+      if ((api.lib = dlopen(nme, RTLD_NOW | RTLD_GLOBAL)))
+        break;
+    if (api.lib)
+    {
+      api.GetUniqueId = (decltype(api.GetUniqueId)) dlsym(api.lib, "ncclGetUniqueId");
+      api.CommInitRank = (decltype(api.CommInitRank)) dlsym(api.lib, "ncclCommInitRank");
+      api.AllGather = (decltype(api.AllGather)) dlsym(api.lib, "ncclAllGather");
+      api.CommDestroy = (decltype(api.CommDestroy)) dlsym(api.lib, "ncclCommDestroy");
+      api.CommCount = (decltype(api.CommCount)) dlsym(api.lib, "ncclCommCount");
+      api.CommUserRank = (decltype(api.CommUserRank)) dlsym(api.lib, "ncclCommUserRank");
+      api.GetErrorString = (decltype(api.GetErrorString)) dlsym(api.lib, "ncclGetErrorString");
+      if (!api.GetUniqueId || !api.CommInitRank || !api.AllGather || !api.CommDestroy || !api.CommCount ||
+          !api.CommUserRank || !api.GetErrorString)
+        api.lib = nullptr;
+    }
+  }
+  return api.lib ? &api : nullptr;
+}
+#define NC(call)                                                                                          \
+  do                                                                                                      \
+  {                                                                                                       \
+    ncclResult_t r_ = (call);                                                                             \
+    if (r_ != ncclSuccess)                                                                                \
+      return fail(BIOEM_B200_ERR_CUDA, std::string(#call) + ": " + nccl_api()->GetErrorString(r_));       \
+  } while (0)
+
 struct bioem_b200_context
 {
   bioem_b200_config cfg{};
@@ -41,6 +94,7 @@ struct bioem_b200_context
   int A = 0;
   float NormDen = 0.f;
   float4 *d_angles = nullptr;
+  std::vector<float4> h_angles; // host copy (the exact arg-max pass re-projects the winning orientations)
   int O = 0;
   float4 *d_ctf = nullptr;
   double *d_prior = nullptr;
@@ -48,6 +102,7 @@ struct bioem_b200_context
   float4 *d_refs = nullptr;
   float *d_sumRef = nullptr, *d_sumsqRef = nullptr;
   int M = 0;
+  size_t particle_cap = 0; // images the particle / state buffers were allocated for
   float2 *d_tw_inv = nullptr, *d_tw_fwd = nullptr;
   unsigned char *d_wtab = nullptr;
   // batch buffers
@@ -65,10 +120,23 @@ struct bioem_b200_context
   ProbAngleOut *d_angtab = nullptr;
   ProbMapOut *d_out = nullptr;
   bool state_ready = false;
+  bool argmax_exact = true; // false: likelihoods were folded in since the last exact arg-max pass
+  int refine_counts[3] = {0, 0, 0}; // records re-evaluated / displacement corrected / re-evaluation disagreed
   // stats
   long long launches = 0, likelihoods = 0, lik_launches = 0;
+  // optional CUDA-event timing of the fused kernel (off unless bioem_b200_set_kernel_timing(h, 1)):
+  // recorded pairs wait in lik_events until bioem_b200_kernel_time() reads them; events are recycled
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> lik_events;
+  std::vector<cudaEvent_t> event_pool;
   bool time_kernels = false;
+  // model points that fell out of the frame, per orientation, since reset (bioem.cpp:1724-1734,1756-1780)
+  int *d_skipped = nullptr;
+  // multi-GPU merge (NCCL communicator, gather buffers)
+  void *nccl_comm = nullptr;
+  bool nccl_owned = false;
+  int nccl_ranks = 0, nccl_rank = 0;
+  Running *d_gather = nullptr;
+  size_t gather_cap = 0;
 };
 
 // Device buffers come from the device's stream-ordered memory pool (cudaMallocAsync on the
@@ -78,6 +146,55 @@ static void dfree(bioem_b200_context *h, void *p)
 {
   if (p)
     cudaFreeAsync(p, h->stream);
+}
+
+// (re)allocate a device array of the handle: the old block is released and the pointer cleared FIRST, so
+// that a failed allocation never leaves a dangling pointer behind (the handle stays destroyable)
+template <class T> static int dev_realloc(bioem_b200_context *h, T *&p, size_t count)
+{
+  dfree(h, p);
+  p = nullptr;
+  if (count == 0)
+    return BIOEM_B200_OK;
+  CU(cudaMallocAsync((void **) &p, sizeof(T) * count, h->stream));
+  return BIOEM_B200_OK;
+}
+
+// temporary device buffer of one entry point: released on every return path
+struct DevTmp
+{
+  bioem_b200_context *h;
+  void *p = nullptr;
+  explicit DevTmp(bioem_b200_context *h_) : h(h_) {}
+  DevTmp(const DevTmp &) = delete;
+  DevTmp &operator=(const DevTmp &) = delete;
+  ~DevTmp()
+  {
+    if (p)
+      cudaFreeAsync(p, h->stream);
+  }
+  int alloc(size_t bytes)
+  {
+    CU(cudaMallocAsync(&p, bytes ? bytes : 1, h->stream));
+    return BIOEM_B200_OK;
+  }
+  template <class T> T *as() const { return static_cast<T *>(p); }
+};
+#define RC(call)                                                                                          \
+  do                                                                                                      \
+  {                                                                                                       \
+    int rc_ = (call);                                                                                     \
+    if (rc_ != BIOEM_B200_OK)                                                                             \
+      return rc_;                                                                                         \
+  } while (0)
+
+static void nccl_release(bioem_b200_context *h)
+{
+  if (h->nccl_comm && h->nccl_owned && nccl_api())
+    nccl_api()->CommDestroy((ncclComm_t) h->nccl_comm);
+  h->nccl_comm = nullptr;
+  h->nccl_owned = false;
+  h->nccl_ranks = 0;
 }
 
 static void free_batch(bioem_b200_context *h)
@@ -165,10 +282,10 @@ static cudaError_t launch_fft2d(const float *imgs, const double *tempden, int nb
 }
 template <int N>
 static cudaError_t launch_conv(const float4 *proj, const float4 *ctf, const double *prior, float4 *conv, ConvParam *cpar, int C,
-                               int OBcur, float Nt, cudaStream_t s)
+                               int OBcur, float Nt, cudaStream_t s, const int4 *sel, int nsel)
 {
-  dim3 g(C, OBcur);
-  ctf_conv_kernel<N><<<g, NT, 0, s>>>(proj, ctf, prior, conv, cpar, C, Nt);
+  dim3 g(sel ? 1 : C, sel ? nsel : OBcur);
+  ctf_conv_kernel<N><<<g, NT, 0, s>>>(proj, ctf, prior, conv, cpar, C, Nt, sel);
   return cudaGetLastError();
 }
 // dynamic + (an upper bound of the) static shared memory of the fused kernel
@@ -215,13 +332,13 @@ static cudaError_t do_fft2d(int N, const float *imgs, const double *tempden, int
   return cudaErrorInvalidValue;
 }
 static cudaError_t do_conv(int N, const float4 *proj, const float4 *ctf, const double *prior, float4 *conv, ConvParam *cpar,
-                           int C, int OBcur, float Nt, cudaStream_t s)
+                           int C, int OBcur, float Nt, cudaStream_t s, const int4 *sel = nullptr, int nsel = 0)
 {
   switch (N)
   {
 #define X(n)                                                                                              \
   case n:                                                                                                 \
-    return launch_conv<n>(proj, ctf, prior, conv, cpar, C, OBcur, Nt, s);
+    return launch_conv<n>(proj, ctf, prior, conv, cpar, C, OBcur, Nt, s, sel, nsel);
     BIOEM_SIZES(X)
 #undef X
   }
@@ -282,13 +399,14 @@ static int set_ctf_priors(bioem_b200_context *h, const float *CtfParam4, int C)
     }
     prior[c] = pr;
   }
-  dfree(h, h->d_prior);
-  h->d_prior = nullptr;
-  CU(cudaMallocAsync((void **) &h->d_prior, sizeof(double) * C, h->stream));
+  const int Cold = h->C;
+  h->C = 0; // stays 0 (run() refuses) unless everything below succeeds
+  h->state_ready = false;
+  if (C != Cold)
+    free_batch(h);
+  RC(dev_realloc(h, h->d_prior, (size_t) C));
   CU(cudaMemcpyAsync(h->d_prior, prior.data(), sizeof(double) * C, cudaMemcpyHostToDevice, h->stream));
   CU(cudaStreamSynchronize(h->stream));
-  if (C != h->C)
-    free_batch(h);
   h->C = C;
   return BIOEM_B200_OK;
 }
@@ -310,19 +428,74 @@ int bioem_b200_device_count(void)
 }
 int bioem_b200_supported_size(int N) { return map4_for(N) != 0; }
 
+// number of displacement-window points per axis as the reference's Algo 1 enumerates them
+// (bioem_algorithm.h:156-197): 0, G, 2G, .. <= maxD, then N - maxD, N - maxD + G, .. < N, i.e.
+// floor(maxD/G) + 1 non-negative and ceil(maxD/G) negative displacements (quirk Q3: when G does not
+// divide maxD this is NOT the symmetric set NxDisp = 2*(maxD/G)+1 of param.cpp:1614-1617).
+static void window_counts(int maxD, int G, int *npos, int *nneg)
+{
+  *npos = maxD / G + 1;
+  *nneg = (maxD + G - 1) / G;
+}
+
+static int create_impl(bioem_b200_context *h, const bioem_b200_config *cfg)
+{
+  const int N = h->N;
+  CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  {
+    // keep freed blocks in the pool instead of returning them to the driver at every synchronisation
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, h->device) == cudaSuccess)
+    {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+  }
+  // twiddles (double -> float) at [n2*R1 + k1], and the displacement-window table
+  int R1 = 0, R2 = 0;
+  geo_for(N, &R1, &R2);
+  std::vector<float2> twi(N), twf(N);
+  for (int n2 = 0; n2 < R2; n2++)
+    for (int k1 = 0; k1 < R1; k1++)
+    {
+      const long long pr = ((long long) n2 * k1) % N;
+      const double ang = 2.0 * M_PI * (double) pr / (double) N;
+      twi[n2 * R1 + k1] = make_float2((float) cos(ang), (float) sin(ang));
+      twf[n2 * R1 + k1] = make_float2((float) cos(ang), (float) -sin(ang));
+    }
+  std::vector<unsigned char> wt(N, 255);
+  for (int k = 0; k < h->npos; k++)
+    wt[k * cfg->GridSpaceCenter] = (unsigned char) k;
+  for (int k = 0; k < h->nw - h->npos; k++)
+    wt[N - cfg->maxDisplaceCenter + k * cfg->GridSpaceCenter] = (unsigned char) (h->npos + k);
+  RC(dev_realloc(h, h->d_tw_inv, (size_t) N));
+  RC(dev_realloc(h, h->d_tw_fwd, (size_t) N));
+  RC(dev_realloc(h, h->d_wtab, (size_t) N));
+  CU(cudaMemcpyAsync(h->d_tw_inv, twi.data(), sizeof(float2) * N, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaMemcpyAsync(h->d_tw_fwd, twf.data(), sizeof(float2) * N, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaMemcpyAsync(h->d_wtab, wt.data(), N, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return BIOEM_B200_OK;
+}
+
 int bioem_b200_create(const bioem_b200_config *cfg, int device, bioem_b200_handle *out)
 {
   if (!cfg || !out)
     return fail(BIOEM_B200_ERR_INVALID, "null argument");
+  *out = nullptr;
   const int N = cfg->NumberPixels;
   if (!bioem_b200_supported_size(N))
     return fail(BIOEM_B200_ERR_INVALID, "NUMBER_PIXELS " + std::to_string(N) + " is not an instantiated image edge");
-  if (cfg->GridSpaceCenter < 1 || cfg->maxDisplaceCenter < 0 || cfg->maxDisplaceCenter % cfg->GridSpaceCenter != 0)
-    return fail(BIOEM_B200_ERR_INVALID, "DISPLACE_CENTER: grid spacing must be >= 1 and divide the maximum displacement");
+  if (cfg->GridSpaceCenter < 1 || cfg->maxDisplaceCenter < 0)
+    return fail(BIOEM_B200_ERR_INVALID, "DISPLACE_CENTER: grid spacing must be >= 1 and the maximum displacement >= 0");
   if (2 * cfg->maxDisplaceCenter + 1 > N)
     return fail(BIOEM_B200_ERR_INVALID, "DISPLACE_CENTER: window larger than the image");
-  const int npos = cfg->maxDisplaceCenter / cfg->GridSpaceCenter + 1;
-  const int nw = 2 * npos - 1;
+  int npos, nneg;
+  window_counts(cfg->maxDisplaceCenter, cfg->GridSpaceCenter, &npos, &nneg);
+  const int nw = npos + nneg;
   if (nw > 254)
     return fail(BIOEM_B200_ERR_INVALID, "displacement window has more than 254 points per axis");
   int ndev = bioem_b200_device_count();
@@ -343,44 +516,14 @@ int bioem_b200_create(const bioem_b200_config *cfg, int device, bioem_b200_handl
   h->nw = nw;
   h->nwp = nw + (nw & 1);
   h->map4 = map4_for(N);
-  h->time_kernels = getenv("BIOEM_B200_NO_KERNEL_TIMING") == nullptr;
-  CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  h->time_kernels = getenv("BIOEM_B200_KERNEL_TIMING") != nullptr && atoi(getenv("BIOEM_B200_KERNEL_TIMING")) != 0;
+  const int rc = create_impl(h, cfg);
+  if (rc != BIOEM_B200_OK)
   {
-    // keep freed blocks in the pool instead of returning them to the driver at every synchronisation
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess)
-    {
-      unsigned long long keep = ~0ull;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
-    cudaGetLastError();
+    const std::string msg = g_err; // destroy() must not lose the reason
+    bioem_b200_destroy(h);
+    return fail(rc, msg);
   }
-  // twiddles (double -> float) at [n2*R1 + k1], and the displacement-window table
-  int R1 = 0, R2 = 0;
-  geo_for(N, &R1, &R2);
-  std::vector<float2> twi(N), twf(N);
-  for (int n2 = 0; n2 < R2; n2++)
-    for (int k1 = 0; k1 < R1; k1++)
-    {
-      const long long pr = ((long long) n2 * k1) % N;
-      const double ang = 2.0 * M_PI * (double) pr / (double) N;
-      twi[n2 * R1 + k1] = make_float2((float) cos(ang), (float) sin(ang));
-      twf[n2 * R1 + k1] = make_float2((float) cos(ang), (float) -sin(ang));
-    }
-  std::vector<unsigned char> wt(N, 255);
-  for (int k = 0; k < npos; k++)
-    wt[k * cfg->GridSpaceCenter] = (unsigned char) k;
-  for (int k = 0; k < npos - 1; k++)
-    wt[N - cfg->maxDisplaceCenter + k * cfg->GridSpaceCenter] = (unsigned char) (npos + k);
-  CU(cudaMallocAsync((void **) &h->d_tw_inv, sizeof(float2) * N, h->stream));
-  CU(cudaMallocAsync((void **) &h->d_tw_fwd, sizeof(float2) * N, h->stream));
-  CU(cudaMallocAsync((void **) &h->d_wtab, N, h->stream));
-  CU(cudaMemcpyAsync(h->d_tw_inv, twi.data(), sizeof(float2) * N, cudaMemcpyHostToDevice, h->stream));
-  CU(cudaStreamSynchronize(h->stream));
-  CU(cudaMemcpyAsync(h->d_tw_fwd, twf.data(), sizeof(float2) * N, cudaMemcpyHostToDevice, h->stream));
-  CU(cudaStreamSynchronize(h->stream));
-  CU(cudaMemcpyAsync(h->d_wtab, wt.data(), N, cudaMemcpyHostToDevice, h->stream));
-  CU(cudaStreamSynchronize(h->stream));
   *out = h;
   return BIOEM_B200_OK;
 }
@@ -390,13 +533,19 @@ int bioem_b200_destroy(bioem_b200_handle h)
   if (!h)
     return BIOEM_B200_OK;
   cudaSetDevice(h->device);
-  cudaStreamSynchronize(h->stream);
+  if (h->stream)
+    cudaStreamSynchronize(h->stream);
+  nccl_release(h);
   free_batch(h);
   for (auto &ev : h->lik_events)
   {
     cudaEventDestroy(ev.first);
     cudaEventDestroy(ev.second);
   }
+  for (auto &ev : h->event_pool)
+    cudaEventDestroy(ev);
+  dfree(h, h->d_skipped);
+  dfree(h, h->d_gather);
   dfree(h, h->d_xyzr);
   dfree(h, h->d_dens);
   dfree(h, h->d_angles);
@@ -411,8 +560,12 @@ int bioem_b200_destroy(bioem_b200_handle h)
   dfree(h, h->d_state);
   dfree(h, h->d_angtab);
   dfree(h, h->d_out);
-  cudaStreamSynchronize(h->stream);
-  cudaStreamDestroy(h->stream);
+  if (h->stream)
+  {
+    cudaStreamSynchronize(h->stream);
+    cudaStreamDestroy(h->stream);
+  }
+  cudaGetLastError();
   delete h;
   return BIOEM_B200_OK;
 }
@@ -429,10 +582,10 @@ int bioem_b200_upload_model(bioem_b200_handle h, const bioem_b200_model_point *p
     xyzr[i] = make_float4(pts[i].pos[0], pts[i].pos[1], pts[i].pos[2], pts[i].radius);
     dens[i] = pts[i].density;
   }
-  dfree(h, h->d_xyzr);
-  dfree(h, h->d_dens);
-  CU(cudaMallocAsync((void **) &h->d_xyzr, sizeof(float4) * A, h->stream));
-  CU(cudaMallocAsync((void **) &h->d_dens, sizeof(float) * A, h->stream));
+  h->A = 0; // stays 0 (run() refuses) unless everything below succeeds
+  h->state_ready = false; // new inputs: the next run() starts from a fresh per-image state
+  RC(dev_realloc(h, h->d_xyzr, (size_t) A));
+  RC(dev_realloc(h, h->d_dens, (size_t) A));
   CU(cudaMemcpyAsync(h->d_xyzr, xyzr.data(), sizeof(float4) * A, cudaMemcpyHostToDevice, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   CU(cudaMemcpyAsync(h->d_dens, dens.data(), sizeof(float) * A, cudaMemcpyHostToDevice, h->stream));
@@ -447,16 +600,21 @@ int bioem_b200_upload_orientations(bioem_b200_handle h, const float *angles4, in
   if (!h || !angles4 || O <= 0)
     return fail(BIOEM_B200_ERR_INVALID, "upload_orientations: bad argument");
   CU(cudaSetDevice(h->device));
-  dfree(h, h->d_angles);
-  CU(cudaMallocAsync((void **) &h->d_angles, sizeof(float4) * O, h->stream));
-  CU(cudaMemcpyAsync(h->d_angles, angles4, sizeof(float4) * O, cudaMemcpyHostToDevice, h->stream));
-  CU(cudaStreamSynchronize(h->stream));
-  if (O != h->O)
+  const int Oold = h->O;
+  h->O = 0;
+  h->state_ready = false;
+  if (O != Oold)
   {
     dfree(h, h->d_angtab);
     h->d_angtab = nullptr;
-    h->state_ready = false;
+    dfree(h, h->d_skipped);
+    h->d_skipped = nullptr;
+    free_batch(h); // the batch size is clamped to the number of orientations
   }
+  RC(dev_realloc(h, h->d_angles, (size_t) O));
+  CU(cudaMemcpyAsync(h->d_angles, angles4, sizeof(float4) * O, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  h->h_angles.assign(reinterpret_cast<const float4 *>(angles4), reinterpret_cast<const float4 *>(angles4) + O);
   h->O = O;
   return BIOEM_B200_OK;
 }
@@ -468,17 +626,18 @@ int bioem_b200_upload_ctf(bioem_b200_handle h, const float *refCTF, const float 
   CU(cudaSetDevice(h->device));
   const int N = h->N;
   const size_t stdsz = (size_t) N * (N / 2 + 1);
-  float2 *tmp = nullptr;
-  CU(cudaMallocAsync((void **) &tmp, sizeof(float2) * stdsz * C, h->stream));
-  CU(cudaMemcpyAsync(tmp, refCTF, sizeof(float2) * stdsz * C, cudaMemcpyHostToDevice, h->stream));
+  DevTmp tmp(h);
+  RC(tmp.alloc(sizeof(float2) * stdsz * C));
+  CU(cudaMemcpyAsync(tmp.p, refCTF, sizeof(float2) * stdsz * C, cudaMemcpyHostToDevice, h->stream));
   CU(cudaStreamSynchronize(h->stream));
-  dfree(h, h->d_ctf);
-  h->d_ctf = nullptr;
-  CU(cudaMallocAsync((void **) &h->d_ctf, sizeof(float4) * h->map4 * C, h->stream));
-  CU(do_pack(N, tmp, h->d_ctf, C, h->stream));
+  h->state_ready = false;
+  const int Cold = h->C;
+  h->C = 0;
+  RC(dev_realloc(h, h->d_ctf, h->map4 * C));
+  CU(do_pack(N, tmp.as<float2>(), h->d_ctf, C, h->stream));
   h->launches++;
   CU(cudaStreamSynchronize(h->stream));
-  dfree(h, tmp);
+  h->C = Cold;
   return set_ctf_priors(h, CtfParam4, C);
 }
 
@@ -489,46 +648,41 @@ int bioem_b200_upload_ctf_real(bioem_b200_handle h, const float *kernels, const 
   CU(cudaSetDevice(h->device));
   const int N = h->N;
   const size_t n2 = (size_t) N * N;
-  float *d_img = nullptr;
-  float2 *d_scr = nullptr;
-  CU(cudaMallocAsync((void **) &d_img, sizeof(float) * n2 * C, h->stream));
-  CU(cudaMallocAsync((void **) &d_scr, sizeof(float2) * (size_t) N * (N / 2 + 1) * C, h->stream));
-  CU(cudaMemcpyAsync(d_img, kernels, sizeof(float) * n2 * C, cudaMemcpyHostToDevice, h->stream));
+  DevTmp img(h), scr(h);
+  RC(img.alloc(sizeof(float) * n2 * C));
+  RC(scr.alloc(sizeof(float2) * (size_t) N * (N / 2 + 1) * C));
+  CU(cudaMemcpyAsync(img.p, kernels, sizeof(float) * n2 * C, cudaMemcpyHostToDevice, h->stream));
   CU(cudaStreamSynchronize(h->stream));
-  dfree(h, h->d_ctf);
-  h->d_ctf = nullptr;
-  CU(cudaMallocAsync((void **) &h->d_ctf, sizeof(float4) * h->map4 * C, h->stream));
-  CU(do_fft2d(N, d_img, nullptr, 0, 0.f, h->d_tw_fwd, d_scr, h->d_ctf, C, h->stream));
+  h->state_ready = false;
+  const int Cold = h->C;
+  h->C = 0;
+  RC(dev_realloc(h, h->d_ctf, h->map4 * C));
+  CU(do_fft2d(N, img.as<float>(), nullptr, 0, 0.f, h->d_tw_fwd, scr.as<float2>(), h->d_ctf, C, h->stream));
   h->launches += 2;
   CU(cudaStreamSynchronize(h->stream));
-  dfree(h, d_img);
-  dfree(h, d_scr);
+  h->C = Cold;
   return set_ctf_priors(h, CtfParam4, C);
 }
 
-static int set_particle_count(bioem_b200_context *h, int M)
+// Particle buffers for M images.  h->M stays 0 (run() refuses) until the upload that called this has
+// succeeded and set it; a new particle stack always invalidates the running per-image state.
+static int begin_particles(bioem_b200_context *h, int M, size_t *cap)
 {
-  if (M != h->M)
+  h->state_ready = false;
+  const bool same = (size_t) M == *cap && h->d_refs && h->d_sumRef && h->d_sumsqRef && h->d_state && h->d_out;
+  h->M = 0;
+  if (!same)
   {
-    dfree(h, h->d_refs);
-    dfree(h, h->d_sumRef);
-    dfree(h, h->d_sumsqRef);
-    dfree(h, h->d_state);
-    dfree(h, h->d_out);
+    *cap = 0;
     dfree(h, h->d_angtab);
-    h->d_refs = nullptr;
-    h->d_sumRef = h->d_sumsqRef = nullptr;
-    h->d_state = nullptr;
-    h->d_out = nullptr;
     h->d_angtab = nullptr;
-    h->state_ready = false;
     free_batch(h);
-    CU(cudaMallocAsync((void **) &h->d_refs, sizeof(float4) * h->map4 * M, h->stream));
-    CU(cudaMallocAsync((void **) &h->d_sumRef, sizeof(float) * M, h->stream));
-    CU(cudaMallocAsync((void **) &h->d_sumsqRef, sizeof(float) * M, h->stream));
-    CU(cudaMallocAsync((void **) &h->d_state, sizeof(Running) * M, h->stream));
-    CU(cudaMallocAsync((void **) &h->d_out, sizeof(ProbMapOut) * M, h->stream));
-    h->M = M;
+    RC(dev_realloc(h, h->d_refs, h->map4 * (size_t) M));
+    RC(dev_realloc(h, h->d_sumRef, (size_t) M));
+    RC(dev_realloc(h, h->d_sumsqRef, (size_t) M));
+    RC(dev_realloc(h, h->d_state, (size_t) M));
+    RC(dev_realloc(h, h->d_out, (size_t) M));
+    *cap = (size_t) M;
   }
   return BIOEM_B200_OK;
 }
@@ -538,29 +692,26 @@ int bioem_b200_upload_particles(bioem_b200_handle h, const float *maps, int M)
   if (!h || !maps || M <= 0)
     return fail(BIOEM_B200_ERR_INVALID, "upload_particles: bad argument");
   CU(cudaSetDevice(h->device));
-  int rc = set_particle_count(h, M);
-  if (rc)
-    return rc;
+  RC(begin_particles(h, M, &h->particle_cap));
   const int N = h->N;
   const size_t n2 = (size_t) N * N;
   // chunked so that the real-space staging stays small next to 180 GB of HBM
   const int chunk = (int) std::max<size_t>(1, std::min<size_t>((size_t) M, ((size_t) 1 << 30) / (n2 * 4)));
-  float *d_img = nullptr;
-  float2 *d_scr = nullptr;
-  CU(cudaMallocAsync((void **) &d_img, sizeof(float) * n2 * chunk, h->stream));
-  CU(cudaMallocAsync((void **) &d_scr, sizeof(float2) * (size_t) N * (N / 2 + 1) * chunk, h->stream));
+  DevTmp img(h), scr(h);
+  RC(img.alloc(sizeof(float) * n2 * chunk));
+  RC(scr.alloc(sizeof(float2) * (size_t) N * (N / 2 + 1) * chunk));
   for (int m0 = 0; m0 < M; m0 += chunk)
   {
     const int mc = std::min(chunk, M - m0);
-    CU(cudaMemcpyAsync(d_img, maps + (size_t) m0 * n2, sizeof(float) * n2 * mc, cudaMemcpyHostToDevice, h->stream));
-    image_sums_kernel<<<(mc + 63) / 64, 64, 0, h->stream>>>(d_img, (int) n2, mc, h->d_sumRef + m0, h->d_sumsqRef + m0);
+    CU(cudaMemcpyAsync(img.p, maps + (size_t) m0 * n2, sizeof(float) * n2 * mc, cudaMemcpyHostToDevice, h->stream));
+    image_sums_kernel<<<(mc + 63) / 64, 64, 0, h->stream>>>(img.as<float>(), (int) n2, mc, h->d_sumRef + m0, h->d_sumsqRef + m0);
     CU(cudaGetLastError());
-    CU(do_fft2d(N, d_img, nullptr, 0, 0.f, h->d_tw_fwd, d_scr, h->d_refs + (size_t) m0 * h->map4, mc, h->stream));
+    CU(do_fft2d(N, img.as<float>(), nullptr, 0, 0.f, h->d_tw_fwd, scr.as<float2>(), h->d_refs + (size_t) m0 * h->map4, mc,
+                h->stream));
     h->launches += 3;
     CU(cudaStreamSynchronize(h->stream));
   }
-  dfree(h, d_img);
-  dfree(h, d_scr);
+  h->M = M;
   return BIOEM_B200_OK;
 }
 
@@ -569,19 +720,17 @@ int bioem_b200_upload_particles_mrc(bioem_b200_handle h, const float *raw, int M
   if (!h || !raw || M <= 0)
     return fail(BIOEM_B200_ERR_INVALID, "upload_particles_mrc: bad argument");
   CU(cudaSetDevice(h->device));
-  int rc = set_particle_count(h, M);
-  if (rc)
-    return rc;
+  RC(begin_particles(h, M, &h->particle_cap));
   const int N = h->N;
   const size_t n2 = (size_t) N * N;
   const int chunk = (int) std::max<size_t>(1, std::min<size_t>((size_t) M, ((size_t) 1 << 29) / (n2 * 4)));
-  float *d_raw = nullptr, *d_img = nullptr, *d_mean = nullptr, *d_dev = nullptr;
-  float2 *d_scr = nullptr;
-  CU(cudaMallocAsync((void **) &d_raw, sizeof(float) * n2 * chunk, h->stream));
-  CU(cudaMallocAsync((void **) &d_img, sizeof(float) * n2 * chunk, h->stream));
-  CU(cudaMallocAsync((void **) &d_mean, sizeof(float) * chunk, h->stream));
-  CU(cudaMallocAsync((void **) &d_dev, sizeof(float) * chunk, h->stream));
-  CU(cudaMallocAsync((void **) &d_scr, sizeof(float2) * (size_t) N * (N / 2 + 1) * chunk, h->stream));
+  DevTmp t_raw(h), t_img(h), t_mean(h), t_dev(h), t_scr(h);
+  RC(t_raw.alloc(sizeof(float) * n2 * chunk));
+  RC(t_img.alloc(sizeof(float) * n2 * chunk));
+  RC(t_mean.alloc(sizeof(float) * chunk));
+  RC(t_dev.alloc(sizeof(float) * chunk));
+  RC(t_scr.alloc(sizeof(float2) * (size_t) N * (N / 2 + 1) * chunk));
+  float *d_raw = t_raw.as<float>(), *d_img = t_img.as<float>(), *d_mean = t_mean.as<float>(), *d_dev = t_dev.as<float>();
   for (int m0 = 0; m0 < M; m0 += chunk)
   {
     const int mc = std::min(chunk, M - m0);
@@ -592,15 +741,11 @@ int bioem_b200_upload_particles_mrc(bioem_b200_handle h, const float *raw, int M
     mrc_transpose_kernel<<<tg, dim3(32, 8), 0, h->stream>>>(d_raw, d_mean, d_dev, N, normalise, d_img);
     image_sums_kernel<<<(mc + 63) / 64, 64, 0, h->stream>>>(d_img, (int) n2, mc, h->d_sumRef + m0, h->d_sumsqRef + m0);
     CU(cudaGetLastError());
-    CU(do_fft2d(N, d_img, nullptr, 0, 0.f, h->d_tw_fwd, d_scr, h->d_refs + (size_t) m0 * h->map4, mc, h->stream));
+    CU(do_fft2d(N, d_img, nullptr, 0, 0.f, h->d_tw_fwd, t_scr.as<float2>(), h->d_refs + (size_t) m0 * h->map4, mc, h->stream));
     h->launches += 5;
     CU(cudaStreamSynchronize(h->stream));
   }
-  dfree(h, d_raw);
-  dfree(h, d_img);
-  dfree(h, d_mean);
-  dfree(h, d_dev);
-  dfree(h, d_scr);
+  h->M = M;
   return BIOEM_B200_OK;
 }
 
@@ -609,27 +754,25 @@ int bioem_b200_upload_particles_fft(bioem_b200_handle h, const float *fft, const
   if (!h || !fft || !sum || !sumsq || M <= 0)
     return fail(BIOEM_B200_ERR_INVALID, "upload_particles_fft: bad argument");
   CU(cudaSetDevice(h->device));
-  int rc = set_particle_count(h, M);
-  if (rc)
-    return rc;
+  RC(begin_particles(h, M, &h->particle_cap));
   const int N = h->N;
   const size_t stdsz = (size_t) N * (N / 2 + 1);
   const int chunk = (int) std::max<size_t>(1, std::min<size_t>((size_t) M, ((size_t) 1 << 30) / (stdsz * 8)));
-  float2 *tmp = nullptr;
-  CU(cudaMallocAsync((void **) &tmp, sizeof(float2) * stdsz * chunk, h->stream));
+  DevTmp tmp(h);
+  RC(tmp.alloc(sizeof(float2) * stdsz * chunk));
   for (int m0 = 0; m0 < M; m0 += chunk)
   {
     const int mc = std::min(chunk, M - m0);
-    CU(cudaMemcpyAsync(tmp, fft + (size_t) m0 * stdsz * 2, sizeof(float2) * stdsz * mc, cudaMemcpyHostToDevice, h->stream));
-    CU(do_pack(N, tmp, h->d_refs + (size_t) m0 * h->map4, mc, h->stream));
+    CU(cudaMemcpyAsync(tmp.p, fft + (size_t) m0 * stdsz * 2, sizeof(float2) * stdsz * mc, cudaMemcpyHostToDevice, h->stream));
+    CU(do_pack(N, tmp.as<float2>(), h->d_refs + (size_t) m0 * h->map4, mc, h->stream));
     h->launches++;
     CU(cudaStreamSynchronize(h->stream));
   }
-  dfree(h, tmp);
   CU(cudaMemcpyAsync(h->d_sumRef, sum, sizeof(float) * M, cudaMemcpyHostToDevice, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   CU(cudaMemcpyAsync(h->d_sumsqRef, sumsq, sizeof(float) * M, cudaMemcpyHostToDevice, h->stream));
   CU(cudaStreamSynchronize(h->stream));
+  h->M = M;
   return BIOEM_B200_OK;
 }
 
@@ -644,12 +787,21 @@ static int ensure_batch(bioem_b200_context *h)
   // image-fastest, so all images pass over one group before the next), i.e. a few MB.  Measured on
   // cfg2: 15 orientations per launch 18.93, 60: 19.21, 150: 19.26 M likelihoods/s (fewer launch tails).
   size_t budget = (size_t) 1 << 30;
-  if (getenv("BIOEM_B200_CONV_MB"))
-    budget = (size_t) atol(getenv("BIOEM_B200_CONV_MB")) << 20;
+  // experiment knobs; a value that does not parse to a positive number is ignored
+  auto env_pos = [](const char *name) -> long {
+    const char *v = getenv(name);
+    if (!v)
+      return 0;
+    char *end = nullptr;
+    const long x = strtol(v, &end, 10);
+    return (end != v && x > 0) ? x : 0;
+  };
+  if (env_pos("BIOEM_B200_CONV_MB"))
+    budget = (size_t) env_pos("BIOEM_B200_CONV_MB") << 20;
   long ob = (long) (budget / (mapbytes * (size_t) h->C));
   ob = std::max<long>(1, std::min<long>(ob, h->O));
-  if (getenv("BIOEM_B200_OB"))
-    ob = std::max<long>(1, std::min<long>(atol(getenv("BIOEM_B200_OB")), h->O));
+  if (env_pos("BIOEM_B200_OB"))
+    ob = std::max<long>(1, std::min<long>(env_pos("BIOEM_B200_OB"), h->O));
   h->OB = (int) ob;
   // orientations per CTA: amortise the CTA prologue (and the one likelihood per CTA whose first radix pass
   // cannot be run ahead) over >= 64 likelihoods, keep >= 4 waves (cfg2: 1 -> 2 orientations, +0.5 %)
@@ -659,25 +811,28 @@ static int ensure_batch(bioem_b200_context *h)
   const long long cta_slots = h->N <= 128 ? 592 : h->N <= 224 ? 296 : 148; // resident CTAs of the fused kernel per GPU
   while (og > 1 && (long long) h->M * ((h->OB + og - 1) / og) < 4LL * cta_slots)
     og--;
-  if (getenv("BIOEM_B200_OG"))
-    og = std::max(1, atoi(getenv("BIOEM_B200_OG")));
+  if (env_pos("BIOEM_B200_OG"))
+    og = (int) env_pos("BIOEM_B200_OG");
   h->OG = og;
   // bands of image rows per projection CTA: small bands = many CTAs (an orientation batch is only
   // ~15 images), at the price of every warp skipping more model points that miss its rows
   size_t band_budget = 24 * 1024;
-  if (getenv("BIOEM_B200_BAND_KB"))
-    band_budget = (size_t) atol(getenv("BIOEM_B200_BAND_KB")) * 1024;
+  if (env_pos("BIOEM_B200_BAND_KB"))
+    band_budget = (size_t) env_pos("BIOEM_B200_BAND_KB") * 1024;
   h->nbands = (int) (((size_t) N * N * 4 + band_budget - 1) / band_budget);
   h->band_rows = (N + h->nbands - 1) / h->nbands;
   h->nbands = (N + h->band_rows - 1) / h->band_rows;
-  CU(cudaMallocAsync((void **) &h->d_proj, sizeof(float) * (size_t) N * N * h->OB, h->stream));
-  CU(cudaMallocAsync((void **) &h->d_tempden, sizeof(double) * h->nbands * h->OB, h->stream));
-  CU(cudaMallocAsync((void **) &h->d_scratch, sizeof(float2) * (size_t) N * (N / 2 + 1) * h->OB, h->stream));
-  CU(cudaMallocAsync((void **) &h->d_projfft, mapbytes * h->OB, h->stream));
-  CU(cudaMallocAsync((void **) &h->d_conv, mapbytes * (size_t) h->OB * h->C, h->stream));
-  CU(cudaMallocAsync((void **) &h->d_cpar, sizeof(ConvParam) * (size_t) h->OB * h->C, h->stream));
-  h->partials_cap = (size_t) h->M * ((h->OB + h->OG - 1) / h->OG);
-  CU(cudaMallocAsync((void **) &h->d_partials, sizeof(Running) * h->partials_cap, h->stream));
+  const int OB = h->OB;
+  h->OB = 0; // a failed allocation below leaves "no batch buffers" behind, not a half-built set
+  RC(dev_realloc(h, h->d_proj, (size_t) N * N * OB));
+  RC(dev_realloc(h, h->d_tempden, (size_t) h->nbands * OB));
+  RC(dev_realloc(h, h->d_scratch, (size_t) N * (N / 2 + 1) * OB));
+  RC(dev_realloc(h, h->d_projfft, h->map4 * OB));
+  RC(dev_realloc(h, h->d_conv, h->map4 * (size_t) OB * h->C));
+  RC(dev_realloc(h, h->d_cpar, (size_t) OB * h->C));
+  h->partials_cap = (size_t) h->M * ((OB + h->OG - 1) / h->OG);
+  RC(dev_realloc(h, h->d_partials, h->partials_cap));
+  h->OB = OB;
   return BIOEM_B200_OK;
 }
 
@@ -695,35 +850,37 @@ int bioem_b200_reset(bioem_b200_handle h)
       return fail(BIOEM_B200_ERR_STATE, "reset: upload orientations first");
     const size_t n = (size_t) h->O * h->M;
     if (!h->d_angtab)
-      CU(cudaMallocAsync((void **) &h->d_angtab, sizeof(ProbAngleOut) * n, h->stream));
+      RC(dev_realloc(h, h->d_angtab, n));
     init_angles_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, h->stream>>>(h->d_angtab, n);
     CU(cudaGetLastError());
     h->launches++;
   }
-  for (auto &ev : h->lik_events)
+  if (h->O > 0)
   {
-    cudaEventDestroy(ev.first);
-    cudaEventDestroy(ev.second);
+    if (!h->d_skipped)
+      RC(dev_realloc(h, h->d_skipped, (size_t) h->O));
+    CU(cudaMemsetAsync(h->d_skipped, 0, sizeof(int) * (size_t) h->O, h->stream));
   }
-  h->lik_events.clear();
   h->launches = 0;
   h->likelihoods = 0;
   h->lik_launches = 0;
+  h->argmax_exact = true;
   h->state_ready = true;
   return BIOEM_B200_OK;
 }
 
 // stages 1 + 2 for orientations [o0, o0+OBcur) into the batch buffers
-static int run_front(bioem_b200_context *h, int o0, int OBcur)
+static int run_front(bioem_b200_context *h, int o0, int OBcur, const float4 *angles = nullptr, const int4 *sel = nullptr,
+                     int nsel = 0)
 {
   const int N = h->N;
   ProjParams pp;
   pp.xyzr = h->d_xyzr;
   pp.dens = h->d_dens;
-  pp.angles = h->d_angles;
+  pp.angles = angles ? angles : h->d_angles; // (a private list: the exact arg-max pass)
   pp.proj = h->d_proj;
   pp.tempden = h->d_tempden;
-  pp.skipped = nullptr;
+  pp.skipped = angles ? nullptr : h->d_skipped; // indexed by the absolute orientation number
   pp.A = h->A;
   pp.N = N;
   pp.band_rows = h->band_rows;
@@ -740,7 +897,7 @@ static int run_front(bioem_b200_context *h, int o0, int OBcur)
   project_kernel<<<pg, 256, (size_t) h->band_rows * N * 4, h->stream>>>(pp);
   CU(cudaGetLastError());
   CU(do_fft2d(N, h->d_proj, h->d_tempden, h->nbands, h->NormDen, h->d_tw_fwd, h->d_scratch, h->d_projfft, OBcur, h->stream));
-  CU(do_conv(N, h->d_projfft, h->d_ctf, h->d_prior, h->d_conv, h->d_cpar, h->C, OBcur, h->cfg.Ntotpi, h->stream));
+  CU(do_conv(N, h->d_projfft, h->d_ctf, h->d_prior, h->d_conv, h->d_cpar, h->C, OBcur, h->cfg.Ntotpi, h->stream, sel, nsel));
   h->launches += 4;
   return BIOEM_B200_OK;
 }
@@ -758,6 +915,7 @@ static void fill_lik_params(bioem_b200_context *h, LikParams &lp, int o0, int OB
   lp.partials = h->d_partials;
   lp.angles = h->cfg.writeAngles ? h->d_angtab : nullptr;
   lp.dbg_values = nullptr;
+  lp.pairs = nullptr;
   lp.M = h->M;
   lp.C = h->C;
   lp.OBcur = OBcur;
@@ -801,8 +959,16 @@ int bioem_b200_run(bioem_b200_handle h, int oBegin, int oEnd)
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->time_kernels)
     {
-      CU(cudaEventCreate(&e0));
-      CU(cudaEventCreate(&e1));
+      for (cudaEvent_t *e : {&e0, &e1})
+      {
+        if (!h->event_pool.empty())
+        {
+          *e = h->event_pool.back();
+          h->event_pool.pop_back();
+        }
+        else
+          CU(cudaEventCreate(e));
+      }
       CU(cudaEventRecord(e0, h->stream));
     }
     CU(do_lik(h->N, lp, h->M * NG, h->cfg.maxDisplaceCenter, h->stream));
@@ -816,7 +982,95 @@ int bioem_b200_run(bioem_b200_handle h, int oBegin, int oEnd)
     h->launches += 2;
     h->lik_launches += 1;
     h->likelihoods += (long long) OBcur * h->C * h->M;
+    h->argmax_exact = false;
   }
+  return BIOEM_B200_OK;
+}
+
+// Exact first-of-ties displacement for the arg-max record of every particle (see exact_argmax_kernel): the
+// winning (orientation, CTF) of each particle is evaluated once more by the fused kernel with its correlation
+// window written out, then the reference's rule is applied to all of its displacements.  One extra likelihood
+// per particle on top of nOrient x nCtf: cost below 0.1 % of a run.
+static int refine_argmax(bioem_b200_context *h)
+{
+  if (h->argmax_exact)
+    return BIOEM_B200_OK;
+  if (getenv("BIOEM_B200_NO_EXACT_ARGMAX"))
+    return BIOEM_B200_OK;
+  if (h->A <= 0 || h->O <= 0 || h->C <= 0 || h->M <= 0 || (int) h->h_angles.size() != h->O)
+    return BIOEM_B200_OK; // inputs were replaced since the run: nothing to re-evaluate against
+  RC(ensure_batch(h));
+  const int M = h->M;
+  std::vector<Running> st((size_t) M);
+  CU(cudaMemcpyAsync(st.data(), h->d_state, sizeof(Running) * (size_t) M, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  // particles ordered by winning orientation; distinct orientations are projected once
+  std::vector<int> order;
+  order.reserve(M);
+  for (int m = 0; m < M; m++)
+    if (st[m].Const > kMinProb && st[m].orient >= 0 && st[m].orient < h->O && st[m].conv >= 0 && st[m].conv < h->C)
+      order.push_back(m);
+  std::sort(order.begin(), order.end(), [&](int a, int b) {
+    return st[a].orient != st[b].orient ? st[a].orient < st[b].orient : a < b;
+  });
+  const size_t nv = (size_t) h->nw * h->nw;
+  DevTmp t_cnt(h);
+  RC(t_cnt.alloc(sizeof(int) * 3));
+  CU(cudaMemsetAsync(t_cnt.p, 0, sizeof(int) * 3, h->stream));
+  size_t pos = 0;
+  while (pos < order.size())
+  {
+    // one batch: up to OB distinct orientations
+    std::vector<float4> ang;
+    std::vector<RefineItem> items;
+    int last = -1;
+    while (pos < order.size())
+    {
+      const int m = order[pos];
+      // the batch buffers hold OB projections and OB*C conv spectra (one conv slot per item here)
+      if ((st[m].orient != last && (int) ang.size() == h->OB) || items.size() == (size_t) h->OB * h->C)
+        break;
+      if (st[m].orient != last)
+      {
+        ang.push_back(h->h_angles[st[m].orient]);
+        last = st[m].orient;
+      }
+      RefineItem it;
+      it.m = m;
+      it.slot = (int) ang.size() - 1;
+      it.conv = st[m].conv;
+      it.pad = 0;
+      items.push_back(it);
+      pos++;
+    }
+    DevTmp t_ang(h), t_items(h), t_val(h), t_part(h);
+    RC(t_ang.alloc(sizeof(float4) * ang.size()));
+    RC(t_items.alloc(sizeof(RefineItem) * items.size()));
+    RC(t_val.alloc(sizeof(float) * nv * items.size()));
+    RC(t_part.alloc(sizeof(Running) * items.size()));
+    CU(cudaMemcpyAsync(t_ang.p, ang.data(), sizeof(float4) * ang.size(), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(t_items.p, items.data(), sizeof(RefineItem) * items.size(), cudaMemcpyHostToDevice, h->stream));
+    static_assert(sizeof(RefineItem) == sizeof(int4), "work item layout");
+    RC(run_front(h, 0, (int) ang.size(), t_ang.as<float4>(), t_items.as<int4>(), (int) items.size()));
+    LikParams lp;
+    fill_lik_params(h, lp, 0, (int) items.size()); // one "orientation" of one CTF per item
+    lp.C = 1;
+    lp.OG = 1;
+    lp.pairs = t_items.as<int4>();
+    lp.partials = t_part.as<Running>();
+    lp.angles = nullptr;
+    lp.dbg_values = t_val.as<float>();
+    CU(do_lik(h->N, lp, (int) items.size(), h->cfg.maxDisplaceCenter, h->stream));
+    exact_argmax_kernel<<<(unsigned) items.size(), 128, 0, h->stream>>>(t_items.as<RefineItem>(), t_val.as<float>(), h->d_cpar,
+                                                                        h->d_sumRef, h->d_sumsqRef, h->C, h->nw, h->cfg.Ntotpi,
+                                                                        lp.invNN, lp.acoef_d, h->d_state, t_cnt.as<int>());
+    CU(cudaGetLastError());
+    h->launches += 6;
+    CU(cudaStreamSynchronize(h->stream)); // the host vectors of this batch go out of scope
+  }
+  CU(cudaMemcpyAsync(h->refine_counts, t_cnt.p, sizeof(int) * 3, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  h->argmax_exact = true;
   return BIOEM_B200_OK;
 }
 
@@ -838,6 +1092,7 @@ int bioem_b200_download(bioem_b200_handle h, bioem_b200_prob_map *maps_out, bioe
   CU(cudaSetDevice(h->device));
   static_assert(sizeof(ProbMapOut) == sizeof(bioem_b200_prob_map) && sizeof(ProbMapOut) == 40, "result layout");
   static_assert(sizeof(ProbAngleOut) == sizeof(bioem_b200_prob_angle) && sizeof(ProbAngleOut) == 16, "result layout");
+  RC(refine_argmax(h));
   finalize_kernel<<<(h->M + 127) / 128, 128, 0, h->stream>>>(h->d_state, h->d_sumRef, h->M, h->nw, h->npos,
                                                             h->cfg.maxDisplaceCenter, h->cfg.GridSpaceCenter, h->cfg.Ntotpi,
                                                             h->d_out);
@@ -861,16 +1116,14 @@ int bioem_b200_download_top_angles(bioem_b200_handle h, int oBegin, int oEnd, in
   static_assert(sizeof(TopAngleOut) == sizeof(bioem_b200_top_angle) && sizeof(TopAngleOut) == 24, "result layout");
   CU(cudaSetDevice(h->device));
   const size_t n = (size_t) h->M * K;
-  double *d_key = nullptr;
-  TopAngleOut *d_top = nullptr;
-  CU(cudaMallocAsync((void **) &d_key, n * sizeof(double), h->stream));
-  CU(cudaMallocAsync((void **) &d_top, n * sizeof(TopAngleOut), h->stream));
-  top_angles_kernel<<<(h->M + 63) / 64, 64, 0, h->stream>>>(h->d_angtab, h->M, oBegin, oEnd, K, d_key, d_top);
+  DevTmp key(h), top(h);
+  RC(key.alloc(n * sizeof(double)));
+  RC(top.alloc(n * sizeof(TopAngleOut)));
+  top_angles_kernel<<<(h->M + 63) / 64, 64, 0, h->stream>>>(h->d_angtab, h->M, oBegin, oEnd, K, key.as<double>(),
+                                                           top.as<TopAngleOut>());
   CU(cudaGetLastError());
   h->launches++;
-  CU(cudaMemcpyAsync(out, d_top, n * sizeof(TopAngleOut), cudaMemcpyDeviceToHost, h->stream));
-  CU(cudaFreeAsync(d_key, h->stream));
-  CU(cudaFreeAsync(d_top, h->stream));
+  CU(cudaMemcpyAsync(out, top.p, n * sizeof(TopAngleOut), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   return BIOEM_B200_OK;
 }
@@ -897,6 +1150,274 @@ int bioem_b200_import_partials(bioem_b200_handle h, const void *device_gathered,
   CU(cudaGetLastError());
   h->launches += 2;
   h->state_ready = true;
+  h->argmax_exact = false;
+  CU(cudaStreamSynchronize(h->stream));
+  return BIOEM_B200_OK;
+}
+
+// ---------------------------------------------------------------- multi-GPU merge inside the library
+int bioem_b200_merge_peers(bioem_b200_handle *hs, int n)
+{
+  if (!hs || n <= 0 || n > 16)
+    return fail(BIOEM_B200_ERR_INVALID, "merge_peers: 1..16 handles expected");
+  for (int r = 0; r < n; r++)
+    if (!hs[r] || !hs[r]->state_ready || hs[r]->M != hs[0]->M)
+      return fail(BIOEM_B200_ERR_STATE, "merge_peers: every handle must have run over the same particles");
+  bioem_b200_context *d = hs[0];
+  // all blocks must be complete before GPU 0 reads them
+  for (int r = 1; r < n; r++)
+  {
+    CU(cudaSetDevice(hs[r]->device));
+    CU(cudaStreamSynchronize(hs[r]->stream));
+  }
+  CU(cudaSetDevice(d->device));
+  PeerParts parts;
+  parts.n = n;
+  std::vector<DevTmp *> staged;
+  int rc = BIOEM_B200_OK;
+  for (int r = 0; r < n && rc == BIOEM_B200_OK; r++)
+  {
+    parts.p[r] = hs[r]->d_state;
+    if (hs[r]->device == d->device)
+      continue;
+    int can = 0;
+    cudaDeviceCanAccessPeer(&can, d->device, hs[r]->device);
+    if (can)
+    {
+      const cudaError_t e = cudaDeviceEnablePeerAccess(hs[r]->device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+        can = 0;
+      cudaGetLastError();
+    }
+    if (!can)
+    {
+      // no peer mapping (PCIe box without P2P): stage the block with a peer copy instead
+      DevTmp *t = new DevTmp(d);
+      staged.push_back(t);
+      rc = t->alloc(sizeof(Running) * (size_t) d->M);
+      if (rc == BIOEM_B200_OK &&
+          cudaMemcpyPeerAsync(t->p, d->device, hs[r]->d_state, hs[r]->device, sizeof(Running) * (size_t) d->M, d->stream) !=
+              cudaSuccess)
+        rc = fail(BIOEM_B200_ERR_CUDA, "merge_peers: cudaMemcpyPeerAsync failed");
+      parts.p[r] = t->as<Running>();
+    }
+  }
+  if (rc == BIOEM_B200_OK)
+  {
+    DevTmp merged(d);
+    rc = merged.alloc(sizeof(Running) * (size_t) d->M);
+    if (rc == BIOEM_B200_OK)
+    {
+      merge_peers_kernel<<<(d->M + 127) / 128, 128, 0, d->stream>>>(parts, d->M, merged.as<Running>());
+      if (cudaGetLastError() != cudaSuccess ||
+          cudaMemcpyAsync(d->d_state, merged.p, sizeof(Running) * (size_t) d->M, cudaMemcpyDeviceToDevice, d->stream) != cudaSuccess ||
+          cudaStreamSynchronize(d->stream) != cudaSuccess)
+        rc = fail(BIOEM_B200_ERR_CUDA, std::string("merge_peers: ") + cudaGetErrorString(cudaGetLastError()));
+      d->launches += 1;
+      d->argmax_exact = false;
+    }
+  }
+  for (DevTmp *t : staged)
+    delete t;
+  return rc;
+}
+
+int bioem_b200_merge_top_angles_peers(bioem_b200_handle *hs, const int *oBegin, const int *oEnd, int n, int K,
+                                      bioem_b200_top_angle *out)
+{
+  if (!hs || !oBegin || !oEnd || !out || n <= 0 || n > 16 || K <= 0)
+    return fail(BIOEM_B200_ERR_INVALID, "merge_top_angles_peers: bad argument");
+  for (int r = 0; r < n; r++)
+    if (!hs[r] || !hs[r]->state_ready || !hs[r]->cfg.writeAngles || !hs[r]->d_angtab || hs[r]->M != hs[0]->M ||
+        oBegin[r] < 0 || oEnd[r] > hs[r]->O || oBegin[r] > oEnd[r] || (r > 0 && oBegin[r] < oEnd[r - 1]))
+      return fail(BIOEM_B200_ERR_STATE, "merge_top_angles_peers: handles must hold ascending orientation blocks with writeAngles");
+  bioem_b200_context *d = hs[0];
+  const size_t rows = (size_t) d->M * K;
+  // every GPU selects the K best orientations of its block where its angle table lies
+  std::vector<DevTmp *> bufs;
+  PeerLists lists;
+  lists.n = n;
+  int rc = BIOEM_B200_OK;
+  for (int r = 0; r < n && rc == BIOEM_B200_OK; r++)
+  {
+    bioem_b200_context *h = hs[r];
+    if (cudaSetDevice(h->device) != cudaSuccess)
+      rc = fail(BIOEM_B200_ERR_CUDA, "merge_top_angles_peers: cudaSetDevice failed");
+    DevTmp *key = new DevTmp(h), *top = new DevTmp(h);
+    bufs.push_back(key);
+    bufs.push_back(top);
+    if (rc == BIOEM_B200_OK)
+      rc = key->alloc(rows * sizeof(double));
+    if (rc == BIOEM_B200_OK)
+      rc = top->alloc(rows * sizeof(TopAngleOut));
+    if (rc != BIOEM_B200_OK)
+      break;
+    top_angles_kernel<<<(h->M + 63) / 64, 64, 0, h->stream>>>(h->d_angtab, h->M, oBegin[r], oEnd[r], K, key->as<double>(),
+                                                             top->as<TopAngleOut>());
+    h->launches++;
+    if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(h->stream) != cudaSuccess)
+      rc = fail(BIOEM_B200_ERR_CUDA, "merge_top_angles_peers: selection kernel failed");
+    lists.p[r] = top->as<TopAngleOut>();
+  }
+  if (rc == BIOEM_B200_OK && cudaSetDevice(d->device) != cudaSuccess)
+    rc = fail(BIOEM_B200_ERR_CUDA, "merge_top_angles_peers: cudaSetDevice failed");
+  for (int r = 1; r < n && rc == BIOEM_B200_OK; r++)
+  {
+    if (hs[r]->device == d->device)
+      continue;
+    int can = 0;
+    cudaDeviceCanAccessPeer(&can, d->device, hs[r]->device);
+    if (can)
+    {
+      const cudaError_t e = cudaDeviceEnablePeerAccess(hs[r]->device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+        can = 0;
+      cudaGetLastError();
+    }
+    if (!can)
+    {
+      DevTmp *t = new DevTmp(d);
+      bufs.push_back(t);
+      rc = t->alloc(rows * sizeof(TopAngleOut));
+      if (rc == BIOEM_B200_OK && cudaMemcpyPeerAsync(t->p, d->device, lists.p[r], hs[r]->device, rows * sizeof(TopAngleOut),
+                                                     d->stream) != cudaSuccess)
+        rc = fail(BIOEM_B200_ERR_CUDA, "merge_top_angles_peers: cudaMemcpyPeerAsync failed");
+      lists.p[r] = t->as<TopAngleOut>();
+    }
+  }
+  if (rc == BIOEM_B200_OK)
+  {
+    DevTmp key(d), top(d);
+    rc = key.alloc(rows * sizeof(double));
+    if (rc == BIOEM_B200_OK)
+      rc = top.alloc(rows * sizeof(TopAngleOut));
+    if (rc == BIOEM_B200_OK)
+    {
+      merge_top_lists_kernel<<<(d->M + 63) / 64, 64, 0, d->stream>>>(lists, d->M, K, key.as<double>(), top.as<TopAngleOut>());
+      d->launches++;
+      if (cudaGetLastError() != cudaSuccess ||
+          cudaMemcpyAsync(out, top.p, rows * sizeof(TopAngleOut), cudaMemcpyDeviceToHost, d->stream) != cudaSuccess ||
+          cudaStreamSynchronize(d->stream) != cudaSuccess)
+        rc = fail(BIOEM_B200_ERR_CUDA, std::string("merge_top_angles_peers: ") + cudaGetErrorString(cudaGetLastError()));
+    }
+  }
+  for (DevTmp *t : bufs)
+  {
+    cudaSetDevice(t->h->device);
+    delete t;
+  }
+  cudaSetDevice(d->device);
+  return rc;
+}
+
+int bioem_b200_nccl_unique_id(void *id128)
+{
+  if (!id128)
+    return fail(BIOEM_B200_ERR_INVALID, "nccl_unique_id: null argument");
+  NcclApi *a = nccl_api();
+  if (!a)
+    return fail(BIOEM_B200_ERR_STATE, "NCCL (libnccl.so.2) cannot be loaded");
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  ncclUniqueId id;
+  NC(a->GetUniqueId(&id));
+  memcpy(id128, &id, sizeof(id));
+  return BIOEM_B200_OK;
+}
+
+int bioem_b200_nccl_init(bioem_b200_handle h, int nRanks, int rank, const void *id128)
+{
+  if (!h || !id128 || nRanks <= 0 || rank < 0 || rank >= nRanks)
+    return fail(BIOEM_B200_ERR_INVALID, "nccl_init: bad argument");
+  NcclApi *a = nccl_api();
+  if (!a)
+    return fail(BIOEM_B200_ERR_STATE, "NCCL (libnccl.so.2) cannot be loaded");
+  CU(cudaSetDevice(h->device));
+  nccl_release(h);
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  ncclComm_t comm = nullptr;
+  NC(a->CommInitRank(&comm, nRanks, id, rank));
+  h->nccl_comm = comm;
+  h->nccl_owned = true;
+  h->nccl_ranks = nRanks;
+  h->nccl_rank = rank;
+  return BIOEM_B200_OK;
+}
+
+int bioem_b200_nccl_attach(bioem_b200_handle h, void *ncclComm)
+{
+  if (!h || !ncclComm)
+    return fail(BIOEM_B200_ERR_INVALID, "nccl_attach: bad argument");
+  NcclApi *a = nccl_api();
+  if (!a)
+    return fail(BIOEM_B200_ERR_STATE, "NCCL (libnccl.so.2) cannot be loaded");
+  nccl_release(h);
+  int n = 0, r = 0;
+  NC(a->CommCount((ncclComm_t) ncclComm, &n));
+  NC(a->CommUserRank((ncclComm_t) ncclComm, &r));
+  h->nccl_comm = ncclComm;
+  h->nccl_owned = false;
+  h->nccl_ranks = n;
+  h->nccl_rank = r;
+  return BIOEM_B200_OK;
+}
+
+int bioem_b200_merge_nccl(bioem_b200_handle h)
+{
+  if (!h || !h->nccl_comm)
+    return fail(BIOEM_B200_ERR_STATE, "merge_nccl: no communicator (bioem_b200_nccl_init / _attach first)");
+  if (!h->state_ready)
+    return fail(BIOEM_B200_ERR_STATE, "merge_nccl: nothing has been run");
+  CU(cudaSetDevice(h->device));
+  const size_t need = (size_t) h->M * h->nccl_ranks;
+  if (h->gather_cap < need)
+  {
+    h->gather_cap = 0;
+    RC(dev_realloc(h, h->d_gather, need));
+    h->gather_cap = need;
+  }
+  // one all-gather of M x 48 bytes per rank, straight out of the running state, on the handle's own
+  // stream; the fold follows in stream order (no host synchronisation in between)
+  NC(nccl_api()->AllGather(h->d_state, h->d_gather, sizeof(Running) * (size_t) h->M, ncclInt8, (ncclComm_t) h->nccl_comm,
+                           h->stream));
+  init_state_kernel<<<(h->M + 127) / 128, 128, 0, h->stream>>>(h->d_state, h->M);
+  merge_partials_kernel<<<(h->M + 127) / 128, 128, 0, h->stream>>>(h->d_gather, h->nccl_ranks, h->M, h->d_state);
+  CU(cudaGetLastError());
+  h->launches += 2;
+  h->argmax_exact = false;
+  return BIOEM_B200_OK;
+}
+
+int bioem_b200_top_angles_nccl(bioem_b200_handle h, int oBegin, int oEnd, int K, bioem_b200_top_angle *out)
+{
+  if (!h || !out || K <= 0 || oBegin < 0 || oEnd > h->O || oBegin > oEnd)
+    return fail(BIOEM_B200_ERR_INVALID, "top_angles_nccl: bad argument");
+  if (!h->nccl_comm)
+    return fail(BIOEM_B200_ERR_STATE, "top_angles_nccl: no communicator (bioem_b200_nccl_init / _attach first)");
+  if (!h->cfg.writeAngles || !h->d_angtab || !h->state_ready)
+    return fail(BIOEM_B200_ERR_STATE, "top_angles_nccl: writeAngles == 0 or nothing has been run");
+  CU(cudaSetDevice(h->device));
+  const size_t rows = (size_t) h->M * K;
+  const int R = h->nccl_ranks;
+  DevTmp key(h), mine(h), all(h), top(h);
+  RC(key.alloc(rows * sizeof(double)));
+  RC(mine.alloc(rows * sizeof(TopAngleOut)));
+  RC(all.alloc(rows * sizeof(TopAngleOut) * R));
+  RC(top.alloc(rows * sizeof(TopAngleOut)));
+  top_angles_kernel<<<(h->M + 63) / 64, 64, 0, h->stream>>>(h->d_angtab, h->M, oBegin, oEnd, K, key.as<double>(),
+                                                           mine.as<TopAngleOut>());
+  CU(cudaGetLastError());
+  NC(nccl_api()->AllGather(mine.p, all.p, rows * sizeof(TopAngleOut), ncclInt8, (ncclComm_t) h->nccl_comm, h->stream));
+  PeerLists lists;
+  lists.n = R;
+  if (R > 16)
+    return fail(BIOEM_B200_ERR_INVALID, "top_angles_nccl: more than 16 ranks");
+  for (int r = 0; r < R; r++)
+    lists.p[r] = all.as<TopAngleOut>() + (size_t) r * rows;
+  merge_top_lists_kernel<<<(h->M + 63) / 64, 64, 0, h->stream>>>(lists, h->M, K, key.as<double>(), top.as<TopAngleOut>());
+  CU(cudaGetLastError());
+  h->launches += 2;
+  CU(cudaMemcpyAsync(out, top.p, rows * sizeof(TopAngleOut), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   return BIOEM_B200_OK;
 }
@@ -912,6 +1433,14 @@ int bioem_b200_stats(bioem_b200_handle h, long long *launches, long long *likeli
     *launches = h->launches;
   if (likelihoods)
     *likelihoods = h->likelihoods;
+  return BIOEM_B200_OK;
+}
+
+int bioem_b200_set_kernel_timing(bioem_b200_handle h, int on)
+{
+  if (!h)
+    return fail(BIOEM_B200_ERR_INVALID, "null handle");
+  h->time_kernels = on != 0;
   return BIOEM_B200_OK;
 }
 
@@ -932,6 +1461,45 @@ int bioem_b200_kernel_time(bioem_b200_handle h, double *ms, long long *n)
     *ms = t;
   if (n)
     *n = (long long) h->lik_events.size();
+  for (auto &ev : h->lik_events)
+  {
+    h->event_pool.push_back(ev.first);
+    h->event_pool.push_back(ev.second);
+  }
+  h->lik_events.clear();
+  return BIOEM_B200_OK;
+}
+
+int bioem_b200_exact_argmax_info(bioem_b200_handle h, int *evaluated, int *corrected, int *disagreed)
+{
+  if (!h)
+    return fail(BIOEM_B200_ERR_INVALID, "null handle");
+  if (evaluated)
+    *evaluated = h->refine_counts[0];
+  if (corrected)
+    *corrected = h->refine_counts[1];
+  if (disagreed)
+    *disagreed = h->refine_counts[2];
+  return BIOEM_B200_OK;
+}
+
+int bioem_b200_out_of_frame(bioem_b200_handle h, int *perOrient, long long *total)
+{
+  if (!h)
+    return fail(BIOEM_B200_ERR_INVALID, "null handle");
+  if (!h->state_ready || !h->d_skipped)
+    return fail(BIOEM_B200_ERR_STATE, "out_of_frame: nothing has been run");
+  CU(cudaSetDevice(h->device));
+  std::vector<int> tmp((size_t) h->O);
+  CU(cudaMemcpyAsync(tmp.data(), h->d_skipped, sizeof(int) * (size_t) h->O, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  long long t = 0;
+  for (int o = 0; o < h->O; o++)
+    t += tmp[o];
+  if (perOrient)
+    memcpy(perOrient, tmp.data(), sizeof(int) * (size_t) h->O);
+  if (total)
+    *total = t;
   return BIOEM_B200_OK;
 }
 
@@ -975,12 +1543,11 @@ int bioem_b200_debug_convolved(bioem_b200_handle h, int o, int c, float *conv_ou
   const size_t stdsz = (size_t) h->N * (h->N / 2 + 1);
   if (conv_out)
   {
-    float2 *tmp = nullptr;
-    CU(cudaMallocAsync((void **) &tmp, sizeof(float2) * stdsz, h->stream));
-    CU(do_unpack(h->N, h->d_conv + (size_t) c * h->map4, tmp, 1, h->stream));
-    CU(cudaMemcpyAsync(conv_out, tmp, sizeof(float2) * stdsz, cudaMemcpyDeviceToHost, h->stream));
+    DevTmp tmp(h);
+    RC(tmp.alloc(sizeof(float2) * stdsz));
+    CU(do_unpack(h->N, h->d_conv + (size_t) c * h->map4, tmp.as<float2>(), 1, h->stream));
+    CU(cudaMemcpyAsync(conv_out, tmp.p, sizeof(float2) * stdsz, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    dfree(h, tmp);
   }
   ConvParam cp;
   CU(cudaMemcpyAsync(&cp, h->d_cpar + c, sizeof(cp), cudaMemcpyDeviceToHost, h->stream));
@@ -1004,10 +1571,11 @@ int bioem_b200_debug_correlation(bioem_b200_handle h, int o, int c, int m, float
   if (rc)
     return rc;
   const size_t nv = (size_t) h->nw * h->nw;
-  float *d_dbg = nullptr;
-  Running *d_part = nullptr;
-  CU(cudaMallocAsync((void **) &d_dbg, sizeof(float) * nv * h->C, h->stream));
-  CU(cudaMallocAsync((void **) &d_part, sizeof(Running), h->stream));
+  DevTmp t_dbg(h), t_part(h);
+  RC(t_dbg.alloc(sizeof(float) * nv * h->C));
+  RC(t_part.alloc(sizeof(Running)));
+  float *d_dbg = t_dbg.as<float>();
+  Running *d_part = t_part.as<Running>();
   LikParams lp;
   fill_lik_params(h, lp, o, 1);
   lp.refs = h->d_refs + (size_t) m * h->map4;
@@ -1021,8 +1589,6 @@ int bioem_b200_debug_correlation(bioem_b200_handle h, int o, int c, int m, float
   CU(do_lik(h->N, lp, 1, h->cfg.maxDisplaceCenter, h->stream));
   CU(cudaMemcpyAsync(values, d_dbg + (size_t) c * nv, sizeof(float) * nv, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
-  dfree(h, d_dbg);
-  dfree(h, d_part);
   if (nvalues)
     *nvalues = (int) nv;
   return BIOEM_B200_OK;
@@ -1036,12 +1602,11 @@ int bioem_b200_debug_particle(bioem_b200_handle h, int m, float *fft_out, float 
   const size_t stdsz = (size_t) h->N * (h->N / 2 + 1);
   if (fft_out)
   {
-    float2 *tmp = nullptr;
-    CU(cudaMallocAsync((void **) &tmp, sizeof(float2) * stdsz, h->stream));
-    CU(do_unpack(h->N, h->d_refs + (size_t) m * h->map4, tmp, 1, h->stream));
-    CU(cudaMemcpyAsync(fft_out, tmp, sizeof(float2) * stdsz, cudaMemcpyDeviceToHost, h->stream));
+    DevTmp tmp(h);
+    RC(tmp.alloc(sizeof(float2) * stdsz));
+    CU(do_unpack(h->N, h->d_refs + (size_t) m * h->map4, tmp.as<float2>(), 1, h->stream));
+    CU(cudaMemcpyAsync(fft_out, tmp.p, sizeof(float2) * stdsz, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    dfree(h, tmp);
   }
   if (sum)
     CU(cudaMemcpyAsync(sum, h->d_sumRef + m, sizeof(float), cudaMemcpyDeviceToHost, h->stream));

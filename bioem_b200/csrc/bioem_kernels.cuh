@@ -174,7 +174,7 @@ struct ProjParams
   const float4 *angles;
   float *proj;      // [OB][N*N]
   double *tempden;  // [OB][nbands]
-  int *skipped;     // [OB] (points out of frame), optional
+  int *skipped;     // [O] points out of frame per orientation (absolute index), optional
   int A;
   int N;
   int band_rows;
@@ -262,49 +262,73 @@ __global__ void __launch_bounds__(256) project_kernel(ProjParams p)
       s_pt[k] = make_int4(skip ? (int) 0x80000000 : i, j, __float_as_int(radius), __float_as_int(den));
     }
     __syncthreads();
-    for (int k = 0; k < nt; k++)
+    // Each warp looks at 32 points of the tile at once: one ballot tells which of them touch the warp's
+    // rows, and only those are rasterised, lowest index first -- the order of the reference's loop over the
+    // model points, so every pixel still receives its contributions in model order.  (Walking the tile point
+    // by point cost every warp of every band ~10 instructions per point that misses its rows: 2.7 ms per
+    // orientation with the 110,592 voxels of a 48^3 MRC model.)
+    for (int k0 = 0; k0 < nt; k0 += 32)
     {
-      const int4 e = s_pt[k];
-      const int i = e.x, j = e.y;
-      if (i == (int) 0x80000000)
+      int4 e = make_int4((int) 0x80000000, 0, 0, 0);
+      bool hit = false, out = false;
+      if (k0 + lane < nt)
       {
-        nskip++;
-        continue;
-      }
-      const float radius = __int_as_float(e.z), den = __int_as_float(e.w);
-      if (radius <= px)
-      {
-        if (i >= wr0 && i < wr1 && lane == 0)
+        e = s_pt[k0 + lane];
+        out = e.x == (int) 0x80000000;
+        if (!out)
         {
-          band[(i - r0) * N + j] = __fadd_rn(band[(i - r0) * N + j], den);
-          td = __fadd_rn(td, den);
-        }
-      }
-      else
-      {
-        const int irad = (int) __fdiv_rn(radius, px) + 1;
-        if (i + irad < wr0 || i - irad >= wr1)
-          continue;
-        const float rad2 = __fmul_rn(radius, radius);
-        const int S = 2 * irad + 1;
-        const double denom = 4 * 3.14159265358979323846 * (double) radius * (double) rad2;
-        for (int idx = lane; idx < S * S; idx += 32)
-        {
-          const int di = idx / S - irad, dj = idx % S - irad;
-          const int ii = i + di, jj = j + dj;
-          if (ii < wr0 || ii >= wr1)
-            continue;
-          // dist = ((float)(di)*di + dj*dj) * px * px
-          const float dist = __fmul_rn(__fmul_rn(__fadd_rn(__fmul_rn((float) di, (float) di), (float) (dj * dj)), px), px);
-          if (dist < rad2)
+          const float radius = __int_as_float(e.z);
+          if (radius <= px)
+            hit = e.x >= wr0 && e.x < wr1;
+          else
           {
-            const float num = __fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(px, px), 2.f), sqrtf(__fsub_rn(rad2, dist))), den), 3.f);
-            const double w = (double) num / denom;
-            float *px_ = &band[(ii - r0) * N + jj];
-            *px_ = (float) ((double) *px_ + w);
-            td = (float) ((double) td + w);
+            const int irad = (int) __fdiv_rn(radius, px) + 1;
+            hit = !(e.x + irad < wr0 || e.x - irad >= wr1);
           }
         }
+      }
+      nskip += __popc(__ballot_sync(0xffffffffu, out));
+      unsigned todo = __ballot_sync(0xffffffffu, hit);
+      while (todo)
+      {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int i = __shfl_sync(0xffffffffu, e.x, src), j = __shfl_sync(0xffffffffu, e.y, src);
+        const float radius = __int_as_float(__shfl_sync(0xffffffffu, e.z, src));
+        const float den = __int_as_float(__shfl_sync(0xffffffffu, e.w, src));
+        if (radius <= px)
+        {
+          if (lane == 0)
+          {
+            band[(i - r0) * N + j] = __fadd_rn(band[(i - r0) * N + j], den);
+            td = __fadd_rn(td, den);
+          }
+        }
+        else
+        {
+          const int irad = (int) __fdiv_rn(radius, px) + 1;
+          const float rad2 = __fmul_rn(radius, radius);
+          const int S = 2 * irad + 1;
+          const double denom = 4 * 3.14159265358979323846 * (double) radius * (double) rad2;
+          for (int idx = lane; idx < S * S; idx += 32)
+          {
+            const int di = idx / S - irad, dj = idx % S - irad;
+            const int ii = i + di, jj = j + dj;
+            if (ii < wr0 || ii >= wr1)
+              continue;
+            // dist = ((float)(di)*di + dj*dj) * px * px
+            const float dist = __fmul_rn(__fmul_rn(__fadd_rn(__fmul_rn((float) di, (float) di), (float) (dj * dj)), px), px);
+            if (dist < rad2)
+            {
+              const float num = __fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(px, px), 2.f), sqrtf(__fsub_rn(rad2, dist))), den), 3.f);
+              const double w = (double) num / denom;
+              float *px_ = &band[(ii - r0) * N + jj];
+              *px_ = (float) ((double) *px_ + w);
+              td = (float) ((double) td + w);
+            }
+          }
+        }
+        // the next point may touch the same pixels from other lanes: order the read-modify-writes
         __syncwarp();
       }
     }
@@ -325,7 +349,7 @@ __global__ void __launch_bounds__(256) project_kernel(ProjParams p)
       t += (double) s_td[k];
     p.tempden[(size_t) ob * p.nbands + b] = t;
     if (p.skipped && b == 0)
-      p.skipped[ob] = nskip;
+      p.skipped[p.o_base + ob] = nskip; // every thread has counted every out-of-frame point of the model
   }
 }
 
@@ -568,13 +592,19 @@ __global__ void mrc_transpose_kernel(const float *__restrict__ raw, const float 
 template <int N>
 __global__ void __launch_bounds__(NT) ctf_conv_kernel(const float4 *__restrict__ proj, const float4 *__restrict__ ctf,
                                                       const double *__restrict__ prior, float4 *__restrict__ conv,
-                                                      ConvParam *__restrict__ cpar, int C, float Ntotpi)
+                                                      ConvParam *__restrict__ cpar, int C, float Ntotpi,
+                                                      const int4 *__restrict__ sel)
 {
   using L = Lay<N>;
-  const int c = blockIdx.x, ob = blockIdx.y, tid = threadIdx.x;
+  // regular launch: grid (C, orientations of the batch), output slot ob*C + c.  With a selection list (exact
+  // arg-max pass): grid (1, items), item b convolves projection sel[b].y with CTF sel[b].z into slot b.
+  const int tid = threadIdx.x;
+  const int c = sel ? sel[blockIdx.y].z : blockIdx.x;
+  const int ob = sel ? sel[blockIdx.y].y : blockIdx.y;
+  const size_t oslot = sel ? (size_t) blockIdx.y : (size_t) ob * C + c;
   const float4 *P = proj + (size_t) ob * L::MAP4;
   const float4 *K = ctf + (size_t) c * L::MAP4;
-  float4 *V = conv + ((size_t) ob * C + c) * L::MAP4;
+  float4 *V = conv + oslot * L::MAP4;
   float acc = 0.f;
   float sumC = 0.f;
   for (int i = tid; i < L::MAP4; i += NT)
@@ -648,7 +678,7 @@ __global__ void __launch_bounds__(NT) ctf_conv_kernel(const float4 *__restrict__
     cp.sumsqC = ssC;
     const float fl = __fsub_rn(__fmul_rn(ssC, Ntotpi), __fmul_rn(sumC, sumC));
     cp.Bterm = ((double) Ntotpi * 0.5 - 2.0) * log((double) __fsub_rn(Ntotpi, 2.f) * (double) fl) - prior[c];
-    cpar[(size_t) ob * C + c] = cp;
+    cpar[oslot] = cp;
   }
 }
 
@@ -663,7 +693,11 @@ struct LikParams
   const unsigned char *wtab; // [N]  window index of a raw displacement, 255 = outside
   Running *partials;         // [NG][M]
   ProbAngleOut *angles;      // [O][M] or null
-  float *dbg_values;         // optional [OBcur*C][M][nw*nw] correlation values
+  float *dbg_values;         // optional [OBcur*C][M][nw*nw] correlation values ([CTA][nw*nw] with pairs)
+  // optional work list (exact arg-max pass): CTA b evaluates the single likelihood of particle pairs[b].x
+  // against conv spectrum b of the batch (launched with C = 1, OG = 1: the spectra were gathered per item);
+  // its partial goes to partials[b], its correlation window to dbg_values[b]
+  const int4 *pairs;
   int M, C, OBcur, OG, o_base;
   int nw;  // window points per axis
   int nwp; // nw rounded up to even
@@ -877,8 +911,8 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
   const int nw = p.nw, nwp = p.nwp;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float2 *E = Eall + (size_t) warp * SM::EW;
-  const int m = blockIdx.x % p.M;
-  const int g = blockIdx.x / p.M;
+  const int m = p.pairs ? p.pairs[blockIdx.x].x : blockIdx.x % p.M;
+  const int g = p.pairs ? blockIdx.x : blockIdx.x / p.M;
   const int o_lo = g * p.OG;
   const int o_hi = min(p.OBcur, o_lo + p.OG);
 
@@ -1367,7 +1401,7 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
                 if ((vmask >> (t * NK + j)) & 1u)
                 {
                   const int wy = WT[k1 + R1 * k2_of(j)];
-                  float *dv = p.dbg_values + ((size_t) oc * p.M + m) * nw * nw;
+                  float *dv = p.dbg_values + (p.pairs ? (size_t) oc : (size_t) oc * p.M + m) * nw * nw;
                   dv[wa * nw + wy] = y[k2_of(j)].x * p.invNN;
                   if (vb)
                     dv[(wa + 1) * nw + wy] = y[k2_of(j)].y * p.invNN;
@@ -1461,7 +1495,7 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
     r.sumC = s_bk.sC;
     r.sumsqC = s_bk.ssC;
     r.pad = 0;
-    p.partials[(size_t) g * p.M + m] = r;
+    p.partials[p.pairs ? (size_t) blockIdx.x : (size_t) g * p.M + m] = r;
   }
 }
 
@@ -1488,6 +1522,44 @@ __global__ void merge_partials_kernel(const Running *__restrict__ partials, int 
     }
     else
       s.Total += r.Total * exp(r.Const - s.Const);
+  }
+  state[m] = s;
+}
+
+// Multi-GPU merge over peer memory: the per-image states of up to 16 GPUs of one box are read where they
+// lie -- parts.p[r] points into GPU r's memory (peer access over NVLink / NVSwitch; the local GPU's own
+// state for r == self) -- and folded in rank order with the rule of merge_partials_kernel.  Gather and
+// merge are one kernel: M x 48 bytes per peer cross the switch as plain coalesced loads, nothing is staged.
+struct PeerParts
+{
+  const Running *p[16];
+  int n;
+};
+__global__ void merge_peers_kernel(PeerParts parts, int M, Running *__restrict__ state)
+{
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M)
+    return;
+  Running s;
+  s.Const = kMinProb;
+  s.Total = 0.0;
+  s.lpf = 0.f;
+  s.orient = s.conv = s.lin = 0;
+  s.v = s.sumC = s.sumsqC = 0.f;
+  s.pad = 0;
+  for (int r = 0; r < parts.n; r++)
+  {
+    const Running q = parts.p[r][m];
+    if (q.Total <= 0.0 && q.Const <= kMinProb)
+      continue;
+    if (s.Const < q.Const)
+    {
+      const double T = s.Total * exp(s.Const - q.Const) + q.Total;
+      s = q;
+      s.Total = T;
+    }
+    else
+      s.Total += q.Total * exp(q.Const - s.Const);
   }
   state[m] = s;
 }
@@ -1570,6 +1642,157 @@ __global__ void top_angles_kernel(const ProbAngleOut *__restrict__ tab, int M, i
     tt[i].pad = 0;
     tt[i].forAngles = 0.0;
     tt[i].ConstAngle = kMinProb;
+  }
+}
+
+// Merge of per-rank lists of most probable orientations (WRITE_PROB_ANGLES on several GPUs): lists[r] holds
+// rank r's [M][K] rows for ITS block of orientations (blocks ascend with the rank), each sorted as
+// top_angles_kernel leaves it.  Feeding a block's rows in ascending orientation order into the same
+// insertion rule reproduces what one pass over all orientations would have kept: a row dropped from a
+// block's list was beaten by K rows of that block, which also beat it in the global list.
+struct PeerLists
+{
+  const TopAngleOut *p[16];
+  int n;
+};
+__global__ void merge_top_lists_kernel(PeerLists lists, int M, int K, double *__restrict__ key, TopAngleOut *__restrict__ top)
+{
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M)
+    return;
+  double *kk = key + (size_t) m * K;
+  TopAngleOut *tt = top + (size_t) m * K;
+  int n = 0;
+  for (int r = 0; r < lists.n; r++)
+  {
+    const TopAngleOut *src = lists.p[r] + (size_t) m * K;
+    // ascending orientation order within the block: repeatedly take the smallest orientation not yet
+    // taken (K is small: the reference's WRITE_PROB_ANGLES is typically 10-50)
+    int last = -1;
+    for (int it = 0; it < K; it++)
+    {
+      int best = -1, bo = 0x7fffffff;
+      for (int i = 0; i < K; i++)
+      {
+        const int o = src[i].orient;
+        if (o > last && o < bo)
+        {
+          bo = o;
+          best = i;
+        }
+      }
+      if (best < 0)
+        break;
+      last = bo;
+      const TopAngleOut row = src[best];
+      const double lp = log(row.forAngles) + row.ConstAngle;
+      if (n == K && !(kk[K - 1] < lp))
+        continue;
+      int pos = (n < K) ? n : K - 1;
+      while (pos > 0 && !(kk[pos - 1] > lp))
+      {
+        kk[pos] = kk[pos - 1];
+        tt[pos] = tt[pos - 1];
+        pos--;
+      }
+      kk[pos] = lp;
+      tt[pos] = row;
+      if (n < K)
+        n++;
+    }
+  }
+  for (int i = n; i < K; i++)
+  {
+    tt[i].orient = -1;
+    tt[i].pad = 0;
+    tt[i].forAngles = 0.0;
+    tt[i].ConstAngle = kMinProb;
+  }
+}
+
+// Exact arg-max displacement of the winning likelihood of every particle (bioem_algorithm.h:84-96: logpro is
+// narrowed to float BEFORE the comparison, so neighbouring displacements often tie exactly, quirk Q10, and the
+// FIRST one in enumeration order keeps the record).  The fused kernel finds the maximum itself exactly, but
+// among the displacements that tie with it only those that were a thread's own minimum are candidates for
+// "first".  This pass closes that gap: the correlation window of the winning (orientation, CTF) of each
+// particle has been re-evaluated by the same kernel (bit-identical values, LikParams::pairs + dbg_values);
+// one CTA per particle evaluates firstele in the same FP32 operation order, the float-narrowed logpro of
+// every displacement that can possibly tie, and takes the lowest enumeration index among the equals.
+struct RefineItem
+{
+  int m, slot, conv, pad;
+};
+__global__ void __launch_bounds__(128) exact_argmax_kernel(const RefineItem *__restrict__ items, const float *__restrict__ values,
+                                                           const ConvParam *__restrict__ cpar, const float *__restrict__ sumRef,
+                                                           const float *__restrict__ sumsqRef, int C, int nw, float Nt, float invNN,
+                                                           double acoef, Running *__restrict__ state, int *__restrict__ counters)
+{
+  const RefineItem it = items[blockIdx.x];
+  const float *v = values + (size_t) blockIdx.x * nw * nw;
+  const ConvParam cp = cpar[blockIdx.x]; // the conv spectra of this pass were gathered per item
+  const float sR = sumRef[it.m], ssR = sumsqRef[it.m];
+  const float f_a = __fmul_rn(ssR, cp.sumsqC);
+  const float f_b = __fmul_rn(__fmul_rn(2.f, sR), cp.sumC);
+  const float f_c = __fmul_rn(__fmul_rn(ssR, cp.sumC), cp.sumC);
+  const float f_d = __fmul_rn(__fmul_rn(sR, sR), cp.sumsqC);
+  auto firstele = [&](float raw) {
+    // same sequence as the fused kernel's epilogue (value = correlation / N^2 was stored)
+    float f = __fmul_rn(raw, raw);
+    f = __fadd_rn(f_a, -f);
+    f = __fmul_rn(Nt, f);
+    f = __fadd_rn(f, __fmul_rn(f_b, raw));
+    f = __fadd_rn(f, -f_c);
+    f = __fadd_rn(f, -f_d);
+    return f;
+  };
+  __shared__ float s_f[128];
+  __shared__ int s_l[128];
+  const int n = nw * nw, tid = threadIdx.x;
+  float fmin = 3.0e38f;
+  for (int i = tid; i < n; i += 128)
+    fmin = fminf(fmin, firstele(v[i]));
+  s_f[tid] = fmin;
+  __syncthreads();
+  for (int s = 64; s > 0; s >>= 1)
+  {
+    if (tid < s)
+      s_f[tid] = fminf(s_f[tid], s_f[tid + s]);
+    __syncthreads();
+  }
+  fmin = s_f[0];
+  const float lpf = (float) (acoef * log((double) fmin) + cp.Bterm);
+  // logpro falls with firstele: whatever narrows to the same float lies within a few ulps of the minimum;
+  // 2e-5 relative (~170 ulps) is a safe superset to run the double-precision log on
+  const float fthr = fmin + fabsf(fmin) * 2e-5f;
+  int best = 0x7fffffff;
+  for (int i = tid; i < n; i += 128)
+  {
+    const float f = firstele(v[i]);
+    if (f <= fthr && (float) (acoef * log((double) f) + cp.Bterm) == lpf)
+      best = min(best, i);
+  }
+  s_l[tid] = best;
+  __syncthreads();
+  for (int s = 64; s > 0; s >>= 1)
+  {
+    if (tid < s)
+      s_l[tid] = min(s_l[tid], s_l[tid + s]);
+    __syncthreads();
+  }
+  if (tid == 0)
+  {
+    Running r = state[it.m];
+    atomicAdd(&counters[0], 1);
+    if (lpf != r.lpf || s_l[0] == 0x7fffffff)
+      atomicAdd(&counters[2], 1); // re-evaluation disagrees with the record: leave it alone (never expected)
+    else
+    {
+      if (r.lin != s_l[0])
+        atomicAdd(&counters[1], 1);
+      r.lin = s_l[0];
+      r.v = v[s_l[0]];
+      state[it.m] = r;
+    }
   }
 }
 

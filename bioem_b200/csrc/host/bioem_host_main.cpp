@@ -7,8 +7,8 @@
 // Flow = the reference's main.cpp:34-140 / bioem::configure / bioem::run with the main loop
 // (bioem.cpp:763-891) replaced by bioem_b200_run on every GPU of the box: the orientation grid is
 // split in contiguous blocks (the reference's MPI split, bioem.cpp:748-753), one host thread
-// drives one GPU, and the per-image partial results are merged in block order
-// (bioem_b200_merge_host: strict '<', so ties resolve to the lowest orientation like a 1-process run).
+// drives one GPU, and the per-image partial results are merged in block order on the devices, over peer
+// memory (bioem_b200_merge_peers: strict '<', so ties resolve to the lowest orientation like a 1-process run).
 #include "bioem_host.hpp"
 #include <algorithm>
 #include <chrono>
@@ -234,10 +234,14 @@ int main(int argc, char **argv)
   int ndev = bioem_b200_device_count();
   if (ndev == 0)
     fail("no CUDA device: bioEM_b200 has no CPU path");
-  if (opt.gpus > 0)
-    ndev = std::min(ndev, opt.gpus);
+  const int nphys = ndev;
+  // BIOEM_B200_OVERSUBSCRIBE=1: more orientation blocks (handles) than GPUs, block g on GPU g % nphys -- the
+  // multi-GPU code path (blocks, device merge) on a box with fewer GPUs (tests)
+  const bool oversub = getenv("BIOEM_B200_OVERSUBSCRIBE") && atoi(getenv("BIOEM_B200_OVERSUBSCRIBE")) != 0;
+  int want = opt.gpus > 0 ? opt.gpus : ndev;
   if (getenv("BIOEM_B200_GPUS"))
-    ndev = std::max(1, std::min(ndev, atoi(getenv("BIOEM_B200_GPUS"))));
+    want = std::max(1, atoi(getenv("BIOEM_B200_GPUS")));
+  ndev = oversub ? std::min(want, 16) : std::min(ndev, want);
   ndev = std::min(ndev, O); // the reference needs at least one orientation per rank (bioem.cpp:675-678)
 
   bioem_b200_config cfg;
@@ -260,40 +264,40 @@ int main(int argc, char **argv)
   cfg.Priorampcent = par.Priorampcent;
 
   printf("\n+++++++++++++++++++++++++++++++++++++++++++\n");
-  printf("Running on %d B200 GPU%s: %d orientations x %d CTF kernels x %d particles, %d x %d pixels\n", ndev,
-         ndev > 1 ? "s" : "", O, C, nMaps, par.N, par.N);
+  printf("Running %d orientation block%s on %d GPU%s: %d orientations x %d CTF kernels x %d particles, %d x %d pixels\n", ndev,
+         ndev > 1 ? "s" : "", std::min(ndev, nphys), std::min(ndev, nphys) > 1 ? "s" : "", O, C, nMaps, par.N, par.N);
   const auto t1 = std::chrono::steady_clock::now();
 
-  std::vector<std::vector<bioem_b200_prob_map>> parts(ndev, std::vector<bioem_b200_prob_map>(nMaps));
-  // WRITE_PROB_ANGLES: every GPU keeps the K most probable orientations of its block per particle
+  // One host thread drives each GPU through its block of orientations; the per-image results are then merged
+  // ON THE DEVICES: GPU 0 reads the other GPUs' partial states over NVLink peer memory inside the merge kernel
+  // (bioem_b200_merge_peers), and for WRITE_PROB_ANGLES every GPU keeps the K most probable orientations of its
+  // block per particle, merged the same way (bioem_b200_merge_top_angles_peers).
   const int K = cfg.writeAngles;
-  std::vector<std::vector<bioem_b200_top_angle>> tops(ndev);
+  std::vector<bioem_b200_handle> handles(ndev, nullptr);
+  std::vector<int> oB(ndev), oE(ndev);
   std::vector<std::string> errors(ndev);
   auto worker = [&](int g) {
     const int o0 = (int) ((long long) g * O / ndev), o1 = (int) ((long long) (g + 1) * O / ndev);
+    oB[g] = o0;
+    oE[g] = o1;
     bioem_b200_handle h = nullptr;
     auto chk = [&](int rc, const char *what) {
       if (rc != BIOEM_B200_OK && errors[g].empty())
         errors[g] = std::string(what) + ": " + bioem_b200_last_error();
       return rc == BIOEM_B200_OK;
     };
-    if (K)
-      tops[g].resize((size_t) nMaps * K);
-    bool ok = chk(bioem_b200_create(&cfg, g, &h), "create") &&
-              chk(bioem_b200_upload_model(h, pts.data(), (int) pts.size(), NormDen), "upload_model") &&
-              chk(bioem_b200_upload_orientations(h, par.angles.data(), O), "upload_orientations") &&
-              chk(par.usepsf ? bioem_b200_upload_ctf_real(h, par.psfKernels.data(), par.CtfParam.data(), C)
-                             : bioem_b200_upload_ctf(h, par.refCTF.data(), par.CtfParam.data(), C),
-                  "upload_ctf") &&
-              chk(rawMRC ? bioem_b200_upload_particles_mrc(h, maps.data(), nMaps, par.notnormmap ? 0 : 1)
-                         : bioem_b200_upload_particles(h, maps.data(), nMaps),
-                  "upload_particles") &&
-              chk(bioem_b200_reset(h), "reset") && chk(bioem_b200_run(h, o0, o1), "run") &&
-              chk(bioem_b200_download(h, parts[g].data(), nullptr), "download");
-    if (ok && K)
-      chk(bioem_b200_download_top_angles(h, o0, o1, K, tops[g].data()), "download_top_angles");
-    if (h)
-      bioem_b200_destroy(h);
+    chk(bioem_b200_create(&cfg, g % nphys, &h), "create") &&
+        chk(bioem_b200_upload_model(h, pts.data(), (int) pts.size(), NormDen), "upload_model") &&
+        chk(bioem_b200_upload_orientations(h, par.angles.data(), O), "upload_orientations") &&
+        chk(par.usepsf ? bioem_b200_upload_ctf_real(h, par.psfKernels.data(), par.CtfParam.data(), C)
+                       : bioem_b200_upload_ctf(h, par.refCTF.data(), par.CtfParam.data(), C),
+            "upload_ctf") &&
+        chk(rawMRC ? bioem_b200_upload_particles_mrc(h, maps.data(), nMaps, par.notnormmap ? 0 : 1)
+                   : bioem_b200_upload_particles(h, maps.data(), nMaps),
+            "upload_particles") &&
+        chk(bioem_b200_reset(h), "reset") && chk(bioem_b200_run(h, o0, o1), "run") &&
+        chk(bioem_b200_synchronize(h), "synchronize");
+    handles[g] = h;
   };
   std::vector<std::thread> th;
   for (int g = 0; g < ndev; g++)
@@ -304,24 +308,42 @@ int main(int argc, char **argv)
     if (!errors[g].empty())
       fail("GPU %d: %s", g, errors[g].c_str());
 
-  std::vector<bioem_b200_prob_map> flat((size_t) ndev * nMaps), pm(nMaps);
+  // the reference warns once per projection that loses model points (bioem.cpp:1724-1734,1756-1780)
+  {
+    std::vector<int> per(O);
+    for (int g = 0; g < ndev; g++)
+    {
+      long long tot = 0;
+      B200(bioem_b200_out_of_frame(handles[g], per.data(), &tot));
+      for (int o = oB[g]; o < oE[g] && tot > 0; o++)
+        if (per[o] > 0)
+          printf("Warning - Projection %d (rank %d): point out of image size. Please check that the input model is "
+                 "correct. (%d model points skipped)\n",
+                 0, o, per[o]);
+    }
+  }
+
+  std::vector<bioem_b200_prob_map> pm(nMaps);
+  B200(bioem_b200_merge_peers(handles.data(), ndev));
+  B200(bioem_b200_download(handles[0], pm.data(), nullptr));
+  const int nCand = K;
+  std::vector<bioem_b200_top_angle> cand((size_t) nMaps * nCand);
+  if (K)
+  {
+    B200(bioem_b200_merge_top_angles_peers(handles.data(), oB.data(), oE.data(), ndev, K, cand.data()));
+    // the writer feeds its heap in ascending orientation order
+    for (int m = 0; m < nMaps; m++)
+    {
+      bioem_b200_top_angle *row = &cand[(size_t) m * nCand];
+      std::stable_sort(row, row + nCand, [](const bioem_b200_top_angle &a, const bioem_b200_top_angle &b) {
+        return (unsigned) a.orient < (unsigned) b.orient; // -1 (unused) last
+      });
+    }
+  }
   for (int g = 0; g < ndev; g++)
-    std::copy(parts[g].begin(), parts[g].end(), flat.begin() + (size_t) g * nMaps);
-  B200(bioem_b200_merge_host(flat.data(), ndev, nMaps, pm.data()));
+    bioem_b200_destroy(handles[g]);
   const auto t2 = std::chrono::steady_clock::now();
 
-  // candidate rows per particle in ascending orientation order (blocks ascend with the GPU index)
-  const int nCand = K * ndev;
-  std::vector<bioem_b200_top_angle> cand((size_t) nMaps * nCand);
-  for (int m = 0; m < nMaps && K; m++)
-  {
-    bioem_b200_top_angle *row = &cand[(size_t) m * nCand];
-    for (int g = 0; g < ndev; g++)
-      std::copy(tops[g].begin() + (size_t) m * K, tops[g].begin() + (size_t) (m + 1) * K, row + (size_t) g * K);
-    std::stable_sort(row, row + nCand, [](const bioem_b200_top_angle &a, const bioem_b200_top_angle &b) {
-      return (unsigned) a.orient < (unsigned) b.orient; // -1 (unused) last
-    });
-  }
   write_outputs(opt, par, cfg, pm, cand, nCand, nMaps);
   const auto t3 = std::chrono::steady_clock::now();
   auto sec = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {

@@ -393,9 +393,11 @@ void read_parameters(const std::string &file, Params &p)
   }
   if (p.writeCTF && !p.usepsf)
     fail("Writing CTF is only valid when integrating over the PSF");
-  if (p.GridSpaceCenter < 1 || p.maxDisplaceCenter % p.GridSpaceCenter != 0)
-    fail("DISPLACE_CENTER: the grid spacing must divide the maximum displacement on the B200 path "
-         "(the reference's two algorithms enumerate different displacement sets otherwise)");
+  // (a spacing that does not divide the maximum displacement is fine: the library enumerates the window of
+  // the reference's Algo 1, bioem_algorithm.h:156-197; the reference itself divides by the spacing,
+  // param.cpp:1614, so 0 is not a usable value there either)
+  if (p.GridSpaceCenter < 1)
+    fail("DISPLACE_CENTER: the grid spacing must be at least 1");
 }
 
 // --------------------------------------------------------------------------- orientations

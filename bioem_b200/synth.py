@@ -61,6 +61,45 @@ def make_model(n_points: int = 1000, seed: int = 1, sigma: float = 18.0,
     return np.round(m, 4)
 
 
+def make_volume(edge: int = 48, seed: int = 2) -> np.ndarray:
+    """float32 [nx,ny,nz] density map for the MRC-volume model (cfg 4): two Gaussian blobs on a
+    5 % noise floor, clipped at 0."""
+    rng = np.random.default_rng(seed)
+    g = (np.arange(edge) + 0.5) / edge - 0.5
+    x, y, z = np.meshgrid(g, g, g, indexing="ij")
+    v = np.exp(-((x + 0.12) ** 2 + (y - 0.05) ** 2 + (z + 0.08) ** 2) / (2 * 0.11 ** 2))
+    v += 0.8 * np.exp(-((x - 0.16) ** 2 + (y + 0.1) ** 2 + (z - 0.12) ** 2) / (2 * 0.08 ** 2))
+    v += 0.05 * rng.normal(size=v.shape)
+    return np.clip(v, 0.0, None).astype(np.float32)
+
+
+def volume_to_points(vol: np.ndarray, px: float) -> np.ndarray:
+    """[A,5] rows x y z radius density exactly as the reference's --ReadModelMRC reader makes them
+    (model.cpp:375-396): one point per voxel, file order (first index outermost), 1-based indices,
+    position (i - nx/2.0)*px, radius 2*px, density = voxel."""
+    nx, ny, nz = vol.shape
+    i, j, k = np.meshgrid(np.arange(1, nx + 1), np.arange(1, ny + 1), np.arange(1, nz + 1), indexing="ij")
+    pos = np.stack([(i - nx / 2.0) * px, (j - ny / 2.0) * px, (k - nz / 2.0) * px], axis=-1).reshape(-1, 3)
+    a = pos.shape[0]
+    return np.column_stack([pos, np.full(a, 2.0 * px), vol.reshape(-1).astype(np.float64)])
+
+
+def write_volume_mrc(path: str, vol: np.ndarray) -> None:
+    """Mode-2 MRC volume in the element order the reference's reader consumes (model.cpp:375-381: the first
+    index is the outermost loop over the file's floats)."""
+    nx, ny, nz = vol.shape
+    hdr = bytearray(1024)
+    struct.pack_into("<4i", hdr, 0, nx, ny, nz, 2)
+    struct.pack_into("<3i", hdr, 28, nx, ny, nz)
+    struct.pack_into("<3f", hdr, 40, float(nx), float(ny), float(nz))
+    struct.pack_into("<3f", hdr, 52, 90.0, 90.0, 90.0)
+    struct.pack_into("<3i", hdr, 64, 1, 2, 3)
+    hdr[208:212] = b"MAP "
+    with open(path, "wb") as f:
+        f.write(bytes(hdr))
+        f.write(np.ascontiguousarray(vol, dtype="<f4").tobytes())
+
+
 def write_model_text(path: str, model: np.ndarray) -> None:
     with open(path, "w") as f:
         for x, y, z, r, d in model:
@@ -241,6 +280,47 @@ def make_particles(model: np.ndarray, quats: np.ndarray, n: int, px: float, m: i
             im = (im - im.mean()) / im.std()
         imgs[k] = im.astype(np.float32)
         truth[k] = (o, c, dx, dy)
+    return imgs, truth
+
+
+def make_particles_bulk(model: np.ndarray, quats: np.ndarray, n: int, px: float, m: int, max_disp: int,
+                        ctf_params: np.ndarray, n_distinct: int = 256, snr: float = 0.1, seed: int = 100,
+                        normalise: bool = True) -> tuple[np.ndarray, np.ndarray]:
+    """Large stacks for the throughput workloads (cfg 3-5): n_distinct clean signals (orientation, CTF,
+    shift drawn like make_particles), every particle = one of them with its own scale, offset and white
+    noise at the given SNR.  Same statistics per image as make_particles at a fraction of the time."""
+    nd = min(n_distinct, m)
+    sig = np.zeros((nd, n, n), dtype=np.float32)
+    tr = np.zeros((nd, 4), dtype=np.int64)
+    for k in range(nd):
+        rng = np.random.default_rng(seed + k)
+        o = int(rng.integers(0, quats.shape[0]))
+        c = int(rng.integers(0, ctf_params.shape[0]))
+        h = max(max_disp // 2, 0)
+        dx, dy = (int(v) for v in rng.integers(-h, h + 1, size=2))
+        proj = project_numpy(model, quats[o], n, px)
+        amp, pha, env = (float(v) for v in ctf_params[c])
+        f = np.fft.rfft2(proj) * ctf_table_numpy(n, px, amp, pha, env)
+        s_ = np.roll(np.fft.irfft2(f, s=(n, n)), (dx, dy), axis=(0, 1))
+        sig[k] = s_.astype(np.float32)
+        tr[k] = (o, c, dx, dy)
+    imgs = np.empty((m, n, n), dtype=np.float32)
+    truth = np.zeros((m, 4), dtype=np.int64)
+    rng = np.random.default_rng(seed + 7919)
+    sd = sig.reshape(nd, -1).std(axis=1)
+    for k0 in range(0, m, 256):
+        k1 = min(m, k0 + 256)
+        idx = np.arange(k0, k1) % nd
+        scale = rng.uniform(0.5, 2.0, size=(k1 - k0, 1, 1)).astype(np.float32)
+        off = rng.normal(0.0, 1.0, size=(k1 - k0, 1, 1)).astype(np.float32)
+        noise = rng.standard_normal(size=(k1 - k0, n, n), dtype=np.float32)
+        noise *= (scale[:, 0, 0] * sd[idx] / np.sqrt(snr)).astype(np.float32)[:, None, None]
+        im = sig[idx] * scale + off + noise
+        if normalise:
+            im -= im.mean(axis=(1, 2), keepdims=True)
+            im /= im.std(axis=(1, 2), keepdims=True)
+        imgs[k0:k1] = im
+        truth[k0:k1] = tr[idx]
     return imgs, truth
 
 

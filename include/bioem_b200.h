@@ -40,9 +40,10 @@ typedef struct bioem_b200_context *bioem_b200_handle;
  * reference bioem.cpp:1627,1715-1750). */
 typedef struct bioem_b200_config
 {
-  int NumberPixels;      /* N, even; supported: 32 36 48 64 96 128 160 192 224 256 288 320 360 384 400 */
+  int NumberPixels;      /* N, even; see bioem_b200_supported_size() */
   int maxDisplaceCenter; /* DISPLACE_CENTER first value  */
-  int GridSpaceCenter;   /* DISPLACE_CENTER second value; must divide maxDisplaceCenter */
+  int GridSpaceCenter;   /* DISPLACE_CENTER second value (need not divide the first: the window is the one
+                            the reference's Algo 1 enumerates, bioem_algorithm.h:156-197) */
   int writeAngles;       /* WRITE_PROB_ANGLES (0 = off)  */
   int tousepsf;          /* USE_PSF                       */
   int doquater;          /* orientations are quaternions  */
@@ -125,6 +126,10 @@ int bioem_b200_upload_particles_mrc(bioem_b200_handle h, const float *raw, int n
 int bioem_b200_upload_particles_fft(bioem_b200_handle h, const float *RefMapsFFT, const float *sum_RefMap,
                                     const float *sumsquare_RefMap, int nMaps);
 
+/* Every upload_* call invalidates the running per-image state: the next run() starts from a freshly
+ * initialised state (as if reset() had been called), so results of different inputs never mix.  An
+ * upload that fails leaves the handle without that input (run() then refuses with ERR_STATE). */
+
 /* replaces the initialisation loop of bioem::run (reference bioem.cpp:681-699) */
 int bioem_b200_reset(bioem_b200_handle h);
 /* replaces the main loop of bioem::run (reference bioem.cpp:763-891) for orientations
@@ -136,6 +141,12 @@ int bioem_b200_synchronize(bioem_b200_handle h);
  * maps_out[nMaps]; angles_out[nOrient*nMaps] in the reference's layout
  * angle*nMaps+map (map.h:147-150), may be NULL when writeAngles == 0. */
 int bioem_b200_download(bioem_b200_handle h, bioem_b200_prob_map *maps_out, bioem_b200_prob_angle *angles_out);
+/* download() first makes the displacement of every particle's arg-max record exact with respect to the
+ * reference's rule "first maximum of the float-narrowed logpro in enumeration order" (bioem_algorithm.h:84-96,
+ * quirks Q6/Q10): the winning (orientation, CTF) of each particle is evaluated once more and all of its
+ * displacements are compared.  Counts of the last such pass: records re-evaluated, displacement indices that
+ * changed, re-evaluations that did not reproduce the record's logpro (left untouched; never expected). */
+int bioem_b200_exact_argmax_info(bioem_b200_handle h, int *evaluated, int *corrected, int *disagreed);
 /* replaces the host heap of the WRITE_PROB_ANGLES writer (reference bioem.cpp:1254-1290):
  * the K most probable orientations of every particle among the orientations
  * [oBegin, oEnd), selected on the device; out[map*K + i], most probable first, in the order
@@ -152,8 +163,37 @@ int bioem_b200_download_top_angles(bioem_b200_handle h, int oBegin, int oEnd, in
 size_t bioem_b200_partial_bytes(bioem_b200_handle h);
 int bioem_b200_export_partial(bioem_b200_handle h, void *device_dst);
 int bioem_b200_import_partials(bioem_b200_handle h, const void *device_gathered, int nRanks);
-/* same merge on host buffers (used by the single-process multi-GPU host binary) */
+/* same merge on host buffers */
 int bioem_b200_merge_host(const bioem_b200_prob_map *parts, int nRanks, int nMaps, bioem_b200_prob_map *out);
+
+/* The merge inside the library (replaces MPI_Allreduce / MPI_Reduce / MPI_Send of reference
+ * bioem.cpp:909-977; lowest rank wins ties, see above).
+ *
+ * One process, one handle per GPU of the box (the bioEM_b200 binary): handles[0]'s GPU reads the other
+ * GPUs' per-image states over NVLink peer memory inside the merge kernel (gather and fold are one
+ * kernel; a peer copy is used where two GPUs have no peer mapping) and ends up holding the merged state;
+ * download it from handles[0].  handles[] in ascending orientation-block order, n <= 16. */
+int bioem_b200_merge_peers(bioem_b200_handle *handles, int n);
+/* WRITE_PROB_ANGLES with several handles (replaces the angle reduction, reference bioem.cpp:979-1040, and the
+ * writer's heap :1254-1290): every GPU selects the K most probable orientations of its block
+ * [oBegin[r], oEnd[r]) per particle, handles[0]'s GPU merges the lists over peer memory; out[map*K + i]
+ * as bioem_b200_download_top_angles. */
+int bioem_b200_merge_top_angles_peers(bioem_b200_handle *handles, const int *oBegin, const int *oEnd, int n, int K,
+                                      bioem_b200_top_angle *out);
+/* One process per GPU (torchrun / MPI launchers): NCCL, bound at run time (libnccl.so.2).
+ * Either let the library build the communicator -- rank 0 calls bioem_b200_nccl_unique_id(id) (128
+ * bytes), the launcher's own plumbing broadcasts id, every rank calls bioem_b200_nccl_init -- or hand
+ * over an existing ncclComm_t with bioem_b200_nccl_attach (not destroyed by the library). */
+int bioem_b200_nccl_unique_id(void *id128);
+int bioem_b200_nccl_init(bioem_b200_handle h, int nRanks, int rank, const void *id128);
+int bioem_b200_nccl_attach(bioem_b200_handle h, void *ncclComm);
+/* one ncclAllGather of the per-image partials (48 bytes per image and rank) on the handle's stream,
+ * followed in stream order by the fold in rank order: every rank ends up with the merged state.
+ * Collective: every rank of the communicator must call it.  Asynchronous like run(). */
+int bioem_b200_merge_nccl(bioem_b200_handle h);
+/* WRITE_PROB_ANGLES across ranks: device selection of this rank's block [oBegin, oEnd), one all-gather
+ * of K x 24 bytes per image and rank, device merge; every rank receives out[map*K + i]. Collective. */
+int bioem_b200_top_angles_nccl(bioem_b200_handle h, int oBegin, int oEnd, int K, bioem_b200_top_angle *out);
 /* the stream all work of this handle is enqueued on (a cudaStream_t) */
 void *bioem_b200_stream(bioem_b200_handle h);
 /* device pointer to the [nOrient][nMaps] angle table (NULL when writeAngles == 0) */
@@ -161,9 +201,16 @@ void *bioem_b200_device_angles(bioem_b200_handle h);
 
 /* statistics of the last run() calls since reset(): kernels launched, likelihoods */
 int bioem_b200_stats(bioem_b200_handle h, long long *kernel_launches, long long *likelihoods);
-/* cudaEvent-timed duration [ms] of all fused likelihood kernels since reset() and
- * their launch count (for roofline accounting); synchronises the stream */
+/* Optional CUDA-event timing of the fused likelihood kernel (roofline accounting of bench.py / the
+ * profiling tools).  Off by default: run() then records no events.  bioem_b200_kernel_time synchronises
+ * the stream and returns the duration [ms] and number of the launches recorded since its previous call
+ * (or since timing was switched on); it is not affected by reset(). */
+int bioem_b200_set_kernel_timing(bioem_b200_handle h, int on);
 int bioem_b200_kernel_time(bioem_b200_handle h, double *likelihood_ms, long long *likelihood_launches);
+/* Model points that fell outside the image frame and were skipped (reference bioem.cpp:1724-1734,
+ * 1756-1780 prints "point out of image size" once per projection): per orientation since reset()
+ * (perOrient[nOrient], may be NULL) and in total. */
+int bioem_b200_out_of_frame(bioem_b200_handle h, int *perOrient, long long *total);
 
 /* ---- inspection entry points (tests): intermediate products of one orientation ---- */
 /* real-space projection (N*N, already scaled by NormDen/tempden) */

@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 EXE = os.path.join(ROOT, "bioem_b200", "bin", "bioEM_b200")
-LOGP_ATOL = {32: 5e-3, 64: 2e-2, 128: 5e-2, 224: 0.3}
+LOGP_ATOL = {32: 5e-3, 64: 2e-2, 128: 5e-2, 224: 0.3, 360: 1.0}
 
 
 def _run(name, tmp_path, env=None):
@@ -30,7 +30,8 @@ def _run(name, tmp_path, env=None):
     return cd
 
 
-@pytest.mark.parametrize("name", ["toy32", "toy32psf", "toy32opts", "toy32euler", "toy32pts", "toy32clip", "toy32amp", "toy64", "cfg1", "cfg2_slice"])
+@pytest.mark.parametrize("name", ["toy32", "toy32psf", "toy32opts", "toy32euler", "toy32pts", "toy32clip", "toy32amp", "toy32g2odd", "toy32g3",
+                                  "toy64", "cfg1", "cfg2_slice", "cfg4_voxel_slice"])
 def test_binary_output_probabilities_match_reference_golden(name, tmp_path, golden_dir):
     cd = _run(name, tmp_path)
     got_path = tmp_path / "Output_Probabilities"
@@ -102,28 +103,43 @@ def test_binary_ang_prob_matches_reference_golden(name, tmp_path, golden_dir):
 
 
 def test_binary_multi_gpu_split_equals_single(tmp_path):
-    """--Gpus / BIOEM_B200_GPUS: the orientation grid split over several handles (here: several
-    handles on however many GPUs the box has) merges to the single-GPU result."""
-    ndev = api.lib().bioem_b200_device_count()
+    """--Gpus / BIOEM_B200_GPUS: the orientation grid split into blocks, one handle per block, merged ON THE DEVICE
+    (bioem_b200_merge_peers / _merge_top_angles_peers).  On a box with fewer GPUs than blocks the blocks share the
+    GPUs (BIOEM_B200_OVERSUBSCRIBE=1), so the multi-GPU code path is exercised on every box."""
     one = tmp_path / "one"
     one.mkdir()
     _run("toy64", one, env={"BIOEM_B200_GPUS": "1"})
     a = parse_output_probabilities(str(one / "Output_Probabilities"))
-    if ndev >= 2:
-        two = tmp_path / "two"
+    for nblocks in (2, 3):
+        two = tmp_path / f"b{nblocks}"
         two.mkdir()
-        _run("toy64", two, env={"BIOEM_B200_GPUS": "2"})
+        _run("toy64", two, env={"BIOEM_B200_GPUS": str(nblocks), "BIOEM_B200_OVERSUBSCRIBE": "1"})
         b = parse_output_probabilities(str(two / "Output_Probabilities"))
         np.testing.assert_allclose(a["logp"], b["logp"], atol=2e-4)
         for k in ("cent_x", "cent_y", "angles", "env", "defocus"):
             np.testing.assert_array_equal(a[k], b[k])
-        # WRITE_PROB_ANGLES: every GPU keeps its block's most probable orientations, the host merges them
-        o1, o2 = tmp_path / "ang1", tmp_path / "ang2"
+        # WRITE_PROB_ANGLES: every block keeps its most probable orientations, merged on the device
+        o1, o2 = tmp_path / f"ang1_{nblocks}", tmp_path / f"ang{nblocks}"
         o1.mkdir()
         o2.mkdir()
         _run("toy32", o1, env={"BIOEM_B200_GPUS": "1"})
-        _run("toy32", o2, env={"BIOEM_B200_GPUS": "2"})
+        _run("toy32", o2, env={"BIOEM_B200_GPUS": str(nblocks), "BIOEM_B200_OVERSUBSCRIBE": "1"})
         assert open(o1 / "ANG_PROB").read() == open(o2 / "ANG_PROB").read()
+        assert open(o1 / "Output_Probabilities").read() == open(o2 / "Output_Probabilities").read()
+
+
+def test_binary_warns_about_model_points_out_of_frame(tmp_path):
+    """reference bioem.cpp:1724-1734,1756-1780: "point out of image size" once per projection that loses points"""
+    if api.lib().bioem_b200_device_count() == 0:
+        pytest.fail("no CUDA device visible: the gpu-marked tests must run on the B200 box")
+    cd = build_case("toy32clip", str(tmp_path))
+    r = subprocess.run([EXE] + reference_cli(cd), cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0
+    warn = [ln for ln in r.stdout.splitlines() if "point out of image size" in ln]
+    assert 1 <= len(warn) <= cd.case.n_orient
+    cd = build_case("toy32", str(tmp_path / "ok"))
+    r = subprocess.run([EXE] + reference_cli(cd), cwd=tmp_path / "ok", capture_output=True, text=True)
+    assert r.returncode == 0 and "point out of image size" not in r.stdout
 
 
 REF_CUDA = os.path.join(ROOT, "oracle", "_ref", "bioEM_ref_cuda")

@@ -51,7 +51,8 @@ def setups():
         v[3].close()
 
 
-@pytest.mark.parametrize("name", ["toy32", "toy32pts", "toy32clip", "toy36g2", "toy64", "cfg1", "cfg2_slice", "cfg4_slice"])
+@pytest.mark.parametrize("name", ["toy32", "toy32pts", "toy32clip", "toy36g2", "toy64", "cfg1", "cfg2_slice", "cfg4_slice",
+                                  "cfg4_voxel_slice"])
 def test_stage1_projection_matches_oracle(setups, name):
     cd, hi, parts, eng, P = setups(name)
     for o in (0, P.O - 1):
@@ -107,7 +108,7 @@ def _window(P):
     return list(range(0, maxd + 1, G)) + list(range(N - maxd, N, G))
 
 
-@pytest.mark.parametrize("name", ["toy32", "toy36g2", "toy64", "cfg1", "cfg2_slice", "cfg4_slice"])
+@pytest.mark.parametrize("name", ["toy32", "toy32g2odd", "toy32g3", "toy36g2", "toy64", "cfg1", "cfg2_slice", "cfg4_slice"])
 def test_stage3_correlation_window_matches_oracle(setups, name):
     cd, hi, parts, eng, P = setups(name)
     n = cd.case.n_pixels
@@ -144,7 +145,8 @@ def _compare_with_oracle(P, hi, pm, res, n):
     return near
 
 
-@pytest.mark.parametrize("name", ["toy32", "toy32psf", "toy32d0", "toy32full", "toy36g2", "toy64", "cfg1", "cfg2_slice", "cfg4_slice"])
+@pytest.mark.parametrize("name", ["toy32", "toy32psf", "toy32d0", "toy32full", "toy32g2odd", "toy32g3", "toy36g2", "toy64", "cfg1",
+                                  "cfg2_slice", "cfg4_slice", "cfg4_voxel_slice"])
 def test_full_run_matches_oracle(setups, name):
     cd, hi, parts, eng, P = setups(name)
     eng.reset()
@@ -155,7 +157,8 @@ def test_full_run_matches_oracle(setups, name):
     assert len(near) <= max(1, P.M // 3), near
 
 
-@pytest.mark.parametrize("name", ["toy32", "toy32psf", "toy32d0", "toy32full", "toy64", "cfg1", "cfg2_slice"])
+@pytest.mark.parametrize("name", ["toy32", "toy32psf", "toy32d0", "toy32full", "toy32g2odd", "toy32g3", "toy64", "cfg1", "cfg2_slice",
+                                  "cfg4_voxel_slice"])
 def test_full_run_matches_reference_golden(setups, name, golden_dir):
     cd, hi, parts, eng, P = setups(name)
     ref = parse_output_probabilities(os.path.join(golden_dir, name, "Output_Probabilities"))
@@ -176,7 +179,7 @@ def test_full_run_matches_reference_golden(setups, name, golden_dir):
             assert ref["const"][m] - lp_at <= NEAR_TIE[cd.case.n_pixels] + 1e-4
 
 
-@pytest.mark.parametrize("name", ["toy32", "cfg5_slice"])
+@pytest.mark.parametrize("name", ["toy32", "toy32g3", "cfg5_slice"])
 def test_angle_table_matches_oracle(setups, name):
     cd, hi, parts, eng, P = setups(name)
     eng.reset()
@@ -279,6 +282,274 @@ def test_split_runs_accumulate_and_partials_roundtrip(setups):
     np.testing.assert_allclose(merged["Total"], full["Total"], rtol=1e-12)
     for k in ("Constoadd", "cent_x", "cent_y", "orient", "conv", "norm", "mu"):
         np.testing.assert_array_equal(merged[k], full[k])
+
+
+def _equal_records(a, b, total_rtol=1e-12):
+    np.testing.assert_allclose(a["Total"], b["Total"], rtol=total_rtol)
+    for k in ("Constoadd", "cent_x", "cent_y", "orient", "conv", "norm", "mu"):
+        np.testing.assert_array_equal(a[k], b[k])
+
+
+def _engine_with(hi, parts, angles=None, ctf=None, cfg=None):
+    e = api.Engine(cfg if cfg is not None else hi.cfg)
+    e.upload_model(hi.points, hi.NormDen)
+    e.upload_orientations(hi.angles if angles is None else angles)
+    if ctf is not None:
+        e.upload_ctf(*ctf)
+    elif hi.use_psf:
+        e.upload_ctf_real(hi.psf_kernels, hi.CtfParam)
+    else:
+        e.upload_ctf(hi.refCTF, hi.CtfParam)
+    e.upload_particles(parts)
+    return e
+
+
+def test_device_merge_of_rank_partials_equals_single_run(setups):
+    """The multi-GPU data path of bench.py / torchrun (reference MPI reduction bioem.cpp:909-977): every rank's
+    block of orientations is run, its per-image partials exported into ONE device buffer (what the all-gather
+    delivers), imported with the device merge kernel -- bit-identical with the single run.  The orientation list
+    holds every orientation twice, so that each particle's maximum is attained in block 0 AND in a later block with
+    bit-equal logpro: the merge must keep the lowest block (= lowest orientation index, like a 1-process run)."""
+    import torch
+    cd, hi, parts, eng, P = setups("toy64")
+    dup = np.ascontiguousarray(np.concatenate([hi.angles[:16], hi.angles[:16], hi.angles[:16]]))
+    O = dup.shape[0]
+    e = _engine_with(hi, parts, angles=dup)
+    try:
+        e.reset()
+        e.run()
+        full, _ = e.download()
+        assert (full["orient"] < 16).all()  # first of the three bit-equal maxima
+        for world in (2, 3, 5):
+            pb = e.partial_bytes()
+            gathered = torch.empty(pb * world, dtype=torch.uint8, device="cuda")
+            for r in range(world):
+                e.reset()
+                e.run(r * O // world, (r + 1) * O // world)
+                e.export_partial(gathered.data_ptr() + r * pb)
+            e.import_partials(gathered.data_ptr(), world)
+            merged, _ = e.download()
+            _equal_records(merged, full)
+    finally:
+        e.close()
+
+
+def test_merge_peers_and_top_angles_over_several_handles(setups):
+    """bioem_b200_merge_peers / _merge_top_angles_peers (the bioEM_b200 binary's multi-GPU path): several handles
+    (one per GPU of the box; all on GPU 0 when there is only one), each with its block of orientations, merged on
+    the device into handles[0] -- equal to the single run, ANG_PROB list included, duplicates resolved like the
+    reference's heap."""
+    cd, hi, parts, eng, P = setups("toy32")
+    ndev = api.lib().bioem_b200_device_count()
+    dup = np.ascontiguousarray(np.concatenate([hi.angles[:9], hi.angles[:9], hi.angles[4:13]]))
+    O = dup.shape[0]
+    single = _engine_with(hi, parts, angles=dup)
+    engines = []
+    try:
+        single.reset()
+        single.run()
+        full, pa = single.download()
+        K = 7
+        top_full = single.download_top_angles(K)
+        for world in (2, 3):
+            engines = []
+            for r in range(world):
+                e = api.Engine(hi.cfg, r % ndev)
+                e.upload_model(hi.points, hi.NormDen)
+                e.upload_orientations(dup)
+                e.upload_ctf(hi.refCTF, hi.CtfParam)
+                e.upload_particles(parts)
+                engines.append(e)
+            blocks = [(r * O // world, (r + 1) * O // world) for r in range(world)]
+            for e, (a, b) in zip(engines, blocks):
+                e.reset()
+                e.run(a, b)
+            api.merge_peers(engines)
+            merged, _ = engines[0].download()
+            _equal_records(merged, full)
+            top = api.merge_top_angles_peers(engines, blocks, K)
+            np.testing.assert_array_equal(top["orient"], top_full["orient"])
+            np.testing.assert_array_equal(top["forAngles"], top_full["forAngles"])
+            np.testing.assert_array_equal(top["ConstAngle"], top_full["ConstAngle"])
+            for e in engines:
+                e.close()
+            engines = []
+    finally:
+        single.close()
+        for e in engines:
+            e.close()
+
+
+def test_merge_nccl_on_a_one_rank_communicator(setups):
+    """bioem_b200_nccl_unique_id / _nccl_init / _merge_nccl / _top_angles_nccl: the library's own NCCL path
+    (libnccl bound at run time) on a communicator of one rank -- the all-gather and the fold must reproduce the
+    state they started from (the N-rank case is bench.py's result_check at --gpus N)."""
+    cd, hi, parts, eng, P = setups("toy32")
+    e = _engine_with(hi, parts)
+    try:
+        e.reset()
+        e.run()
+        before, _ = e.download()
+        top_before = e.download_top_angles(3)
+        e.nccl_init(1, 0, api.nccl_unique_id())
+        e.merge_nccl()
+        after, _ = e.download()
+        _equal_records(after, before, total_rtol=0)
+        top = e.top_angles_nccl(3, 0, P.O)
+        assert top.tobytes() == top_before.tobytes()
+    finally:
+        e.close()
+
+
+def test_uploads_invalidate_the_running_state(setups):
+    """A new particle stack (same count), model, CTF table or orientation list must never be folded into the
+    previous inputs' log-sum-exp: run() after an upload starts from a fresh state (as a new handle would)."""
+    cd, hi, parts, eng, P = setups("toy64")
+    other = np.ascontiguousarray(parts[::-1])
+    e = _engine_with(hi, parts)
+    fresh = _engine_with(hi, other)
+    try:
+        e.run()
+        e.download()
+        e.upload_particles(other)  # same M
+        e.run()
+        got, _ = e.download()
+        fresh.run()
+        want, _ = fresh.download()
+        assert got.tobytes() == want.tobytes()
+        # the same for the model: scaled densities change NormDen but not the normalised projection
+        e.upload_ctf(hi.refCTF[:3], hi.CtfParam[:3])
+        fresh.upload_ctf(hi.refCTF[:3], hi.CtfParam[:3])
+        e.run()
+        fresh.run()
+        assert e.download()[0].tobytes() == fresh.download()[0].tobytes()
+    finally:
+        e.close()
+        fresh.close()
+
+
+def test_out_of_frame_points_are_counted(setups):
+    """reference bioem.cpp:1724-1734,1756-1780: model points that leave the frame are skipped with a warning;
+    the library reports how many per orientation."""
+    cd, hi, parts, eng, P = setups("toy32clip")
+    eng.reset()
+    eng.run()
+    eng.download()
+    per, tot = eng.out_of_frame()
+    assert tot > 0 and per.shape == (P.O,) and int(per.sum()) == tot
+    # count of the oracle's projector for the first orientation: points whose pixel / footprint leaves the frame
+    n, px = cd.case.n_pixels, np.float32(cd.case.pixel_size)
+    from bioem_b200 import synth
+    rot = synth.quat_to_rot(hi.angles[0]).astype(np.float32)
+    xy = (hi.points["pos"].astype(np.float32) @ rot.T)[:, :2]
+    ij = np.floor(xy / px + np.float32(n / 2.0) + np.float32(0.5)).astype(int)
+    rad = hi.points["radius"]
+    irad = (rad / px).astype(int) + 1
+    small = rad <= px
+    out_small = small & ((ij < 0).any(1) | (ij >= n).any(1))
+    out_big = (~small) & ((ij < irad[:, None]).any(1) | (ij >= n - irad[:, None]).any(1))
+    assert abs(int(per[0]) - int(out_small.sum() + out_big.sum())) <= 1  # a point exactly on a pixel edge may round either way
+    cd2, hi2, parts2, eng2, P2 = setups("toy32")
+    eng2.reset()
+    eng2.run()
+    eng2.download()
+    assert eng2.out_of_frame()[1] == 0
+
+
+def _host_first_of_ties(eng, hi, parts_sum, o, c, m, prior):
+    """The reference's rule applied on the host to the GPU's own correlation window of one likelihood:
+    firstele in FP32 in source order (bioem_algorithm.h:29-36), logpro in double, narrowed to float (:84),
+    first maximum in enumeration order (:96)."""
+    f32 = np.float32
+    v = eng.debug_correlation(o, c, m).astype(np.float32).ravel()
+    _, sC, ssC = eng.debug_convolved(o, c)
+    sR, ssR = parts_sum
+    sC, ssC, sR, ssR = f32(sC), f32(ssC), f32(sR), f32(ssR)
+    Nt = f32(hi.cfg.Ntotpi)
+    fe = Nt * (ssR * ssC - v * v) + (f32(2.0) * sR * sC) * v - (ssR * sC) * sC - (sR * sR) * ssC
+    assert fe.dtype == np.float32
+    fl = ssC * Nt - sC * sC
+    a = (3.0 - float(Nt)) * 0.5
+    bterm = (float(Nt) * 0.5 - 2.0) * np.log(float(Nt - f32(2.0)) * float(fl)) - prior
+    lp = (a * np.log(fe.astype(np.float64)) + bterm).astype(np.float32)
+    return int(np.argmax(lp)), lp  # argmax returns the FIRST maximum
+
+
+def test_exact_first_of_ties_displacement():
+    """Quirk Q10: logpro is narrowed to float before the comparison, so displacements tie exactly and the FIRST in
+    enumeration order must win.  A very smooth particle (a wide Gaussian blob) against a smooth model gives a flat
+    correlation peak at N = 224, where one float quantum of logpro spans several ulps of firstele: dozens of
+    displacements tie.  The library's arg-max must be the first of them -- checked against the rule applied on the
+    host to the GPU's own correlation window (so FFT rounding cannot blur the comparison)."""
+    _need_gpu()
+    cd = build_case("cfg2_slice", n_particles=2, n_orient=1)
+    hi, parts = api.inputs_for_case(cd)
+    n = hi.N
+    g = np.arange(n, dtype=np.float64) - n / 2
+    blobs = []
+    for s, (cx, cy) in ((40.0, (3.0, -2.0)), (60.0, (-7.5, 5.5)), (25.0, (0.0, 0.0))):
+        b = np.exp(-((g[:, None] - cx) ** 2 + (g[None, :] - cy) ** 2) / (2 * s * s))
+        blobs.append(((b - b.mean()) / b.std()).astype(np.float32))
+    parts = np.ascontiguousarray(np.stack(blobs))
+    one_ctf = (np.ascontiguousarray(hi.refCTF[5:6]), np.ascontiguousarray(hi.CtfParam[5:6]))
+    e = _engine_with(hi, parts, ctf=one_ctf)
+    try:
+        e.run()
+        pm, _ = e.download()
+        ties = []
+        for m in range(parts.shape[0]):
+            _, sR, ssR = e.debug_particle(m)
+            first, lp = _host_first_of_ties(e, hi, (sR, ssR), 0, 0, m, _prior(hi, one_ctf[1][0]))
+            nw = int(round(np.sqrt(lp.size)))
+            wx, wy = divmod(first, nw)
+            npos = hi.cfg.maxDisplaceCenter // hi.cfg.GridSpaceCenter + 1
+            dx = wx if wx < npos else (wx - npos) - hi.cfg.maxDisplaceCenter
+            dy = wy if wy < npos else (wy - npos) - hi.cfg.maxDisplaceCenter
+            ties.append(int((lp == lp.max()).sum()))
+            assert (int(pm[m]["cent_x"]), int(pm[m]["cent_y"])) == (-dx, -dy), (m, ties, pm[m], (dx, dy))
+            assert pm[m]["Constoadd"] == float(lp.max()), (m, pm[m]["Constoadd"], float(lp.max()))
+        assert max(ties) >= 2, ties  # the case must actually contain exact ties
+        ev, corrected, bad = e.exact_argmax_info()
+        assert ev == parts.shape[0] and bad == 0
+    finally:
+        e.close()
+
+
+def _prior(hi, ctfparam):
+    """prior term of calc_logpro in CTF mode (bioem_algorithm.h:49-56), double like the library's table"""
+    amp, pha, env = (float(x) for x in ctfparam[:3])
+    c = hi.cfg
+    return (env * env / 2. / c.sigmaPriorbctf / c.sigmaPriorbctf
+            - (pha - c.Priordefcent) * (pha - c.Priordefcent) / 2. / c.sigmaPriordefo / c.sigmaPriordefo
+            - (amp - c.Priorampcent) * (amp - c.Priorampcent) / 2. / c.sigmaPrioramp / c.sigmaPrioramp)
+
+
+def test_exact_ties_between_ctfs_orientations_groups_and_launches(monkeypatch, setups):
+    """Quirk Q6: ties between bit-equal likelihoods resolve to the first in enumeration order (orientation
+    ascending, CTF ascending).  Duplicated CTF rows and duplicated orientations give bit-equal logpro; with two
+    orientations per CTA and five per launch the duplicates sit in other CTA groups and other launches of the
+    fused kernel than their originals."""
+    cd, hi, parts, eng, P = setups("toy64")
+    monkeypatch.setenv("BIOEM_B200_OB", "5")
+    monkeypatch.setenv("BIOEM_B200_OG", "2")
+    no, nc = 7, 6
+    dup_angles = np.ascontiguousarray(np.concatenate([hi.angles[:no]] * 3))
+    dup_ctf = (np.ascontiguousarray(np.concatenate([hi.refCTF[:nc]] * 2)), np.ascontiguousarray(np.concatenate([hi.CtfParam[:nc]] * 2)))
+    base = _engine_with(hi, parts, angles=np.ascontiguousarray(hi.angles[:no]),
+                        ctf=(np.ascontiguousarray(hi.refCTF[:nc]), np.ascontiguousarray(hi.CtfParam[:nc])))
+    e = _engine_with(hi, parts, angles=dup_angles, ctf=dup_ctf)
+    try:
+        base.run()
+        want, _ = base.download()
+        e.run()
+        got, _ = e.download()
+        for k in ("Constoadd", "cent_x", "cent_y", "orient", "conv", "norm", "mu"):
+            np.testing.assert_array_equal(got[k], want[k])
+        # six copies of every likelihood: the sum of exp is six times the base's
+        np.testing.assert_allclose(got["Total"], 6.0 * want["Total"], rtol=1e-12)
+    finally:
+        base.close()
+        e.close()
 
 
 def test_particle_upload_paths_agree(setups):

@@ -40,8 +40,12 @@ def test_create_fails_loudly_without_device_or_with_bad_config():
     h = C.c_void_p()
     assert L.bioem_b200_create(C.byref(cfg), 0, C.byref(h)) == 1  # unsupported size
     assert b"NUMBER_PIXELS" in L.bioem_b200_last_error()
-    cfg = api.Config(64, 5, 2, 0, 0, 1, 0, 0, 1.0, 4096, 1.0, 1, 1, 1, 1, 0)
-    assert L.bioem_b200_create(C.byref(cfg), 0, C.byref(h)) == 1  # maxD % G != 0 (quirk Q3)
+    cfg = api.Config(64, 5, 0, 0, 0, 1, 0, 0, 1.0, 4096, 1.0, 1, 1, 1, 1, 0)
+    assert L.bioem_b200_create(C.byref(cfg), 0, C.byref(h)) == 1  # grid spacing 0 (the reference divides by it)
+    assert b"DISPLACE_CENTER" in L.bioem_b200_last_error()
+    cfg = api.Config(64, 40, 1, 0, 0, 1, 0, 0, 1.0, 4096, 1.0, 1, 1, 1, 1, 0)
+    assert L.bioem_b200_create(C.byref(cfg), 0, C.byref(h)) == 1  # window wider than the image
+    # (a spacing that does not divide the maximum displacement is accepted: quirk Q3, Algo 1's window)
     if L.bioem_b200_device_count() == 0:
         cfg = api.Config(64, 4, 1, 0, 0, 1, 0, 0, 1.0, 4096, 1.0, 1, 1, 1, 1, 0)
         rc = L.bioem_b200_create(C.byref(cfg), 0, C.byref(h))

@@ -76,7 +76,7 @@ def _check_against_reference_output(P, res, ref, n):
 
 
 @pytest.mark.parametrize("name", ["toy32", "toy32psf", "toy32d0", "toy32full", "toy32pts", "toy32clip", "toy32amp", "toy36g2", "toy64", "cfg1", "cfg2_slice",
-                                  "cfg5_slice"])
+                                  "cfg5_slice", "toy32g2odd", "toy32g3", "cfg4_voxel_slice"])
 def test_oracle_matches_reference_golden(name, golden_dir):
     cd, P, res = _run_oracle(name)
     ref = parse_output_probabilities(os.path.join(golden_dir, name, "Output_Probabilities"))
@@ -84,7 +84,7 @@ def test_oracle_matches_reference_golden(name, golden_dir):
     _check_against_reference_output(P, res, ref, cd.case.n_pixels)
 
 
-@pytest.mark.parametrize("name", ["toy32", "cfg5_slice"])
+@pytest.mark.parametrize("name", ["toy32", "cfg5_slice", "toy32g3"])
 def test_oracle_angle_table_matches_reference(name, golden_dir):
     cd, P, res = _run_oracle(name)
     ang = parse_ang_prob(os.path.join(golden_dir, name, "ANG_PROB"))

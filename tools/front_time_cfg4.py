@@ -9,14 +9,16 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."
 from bioem_b200 import api  # noqa: E402
 from bioem_b200.cases import CASES, Case, build_case  # noqa: E402
 
-base = CASES["cfg4_slice"]
-npts = int(sys.argv[1]) if len(sys.argv) > 1 else 110592
-n_or = int(sys.argv[2]) if len(sys.argv) > 2 else 8
-cd = build_case(Case(**{**base.__dict__, "n_atoms": npts, "n_particles": 148, "n_orient": n_or}))
+n_or = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+n_pa = int(sys.argv[2]) if len(sys.argv) > 2 else 148
+cd = build_case("cfg4", n_particles=n_pa, n_orient=n_or)  # 48^3 MRC volume = 110,592 points of radius 2 px
+npts = cd.model.shape[0]
 hi, parts = api.inputs_for_case(cd)
 eng = api.Engine(hi.cfg, 0)
 eng.upload_all(hi, parts)
+eng.set_kernel_timing(True)
 eng.reset(); eng.run(0, n_or); eng.synchronize()
+eng.kernel_time()  # drain the warm-up launches
 eng.reset()
 t = time.time(); eng.run(0, n_or); eng.synchronize(); dt = time.time() - t
 ms, n = eng.kernel_time()

@@ -16,9 +16,11 @@ cd = build_case(name, n_particles=n_part, n_orient=n_or if n_part else None)
 hi, parts = api.inputs_for_case(cd)
 eng = api.Engine(hi.cfg, 0)
 eng.upload_all(hi, parts)
+eng.set_kernel_timing(True)
 eng.reset()
 eng.run(0, min(n_or, hi.O))
 eng.synchronize()
+eng.kernel_time()  # drain the warm-up launch
 eng.reset()
 t = time.time()
 eng.run(0, min(n_or, hi.O))

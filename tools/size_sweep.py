@@ -30,8 +30,10 @@ for n in sizes:
         print(f"| {n} | {2 * maxd + 1}² | - | {str(e)[:60]} | | | |")
         continue
     eng.upload_all(hi, parts)
+    eng.set_kernel_timing(True)
     eng.run()
     eng.synchronize()
+    eng.kernel_time()  # drain the warm-up launches
     eng.reset()
     eng.run()
     ms, _ = eng.kernel_time()
