@@ -12,7 +12,7 @@
 
 using namespace bioem;
 
-#define BIOEM_SIZES(X) X(32) X(36) X(48) X(64) X(96) X(128) X(160) X(192) X(224) X(256) X(288) X(320) X(360) X(384) X(400)
+#define BIOEM_SIZES(X) X(32) X(36) X(48) X(64) X(96) X(100) X(120) X(128) X(144) X(160) X(192) X(200) X(216) X(224) X(240) X(256) X(288) X(300) X(320) X(336) X(360) X(384) X(400) X(420) X(432) X(448) X(480) X(500) X(512)
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string &msg)

@@ -310,6 +310,8 @@ template <int N> struct Geo;
     static constexpr int R1 = R1_, R2 = R2_, KC = KC_, PC = PC_;                                   \
     static_assert(R1_ * R2_ == N_ && (R1_ % 2) == 0 && ((N_ / 2) % KC_) == 0, "geometry");         \
   };
+// (R1 even: the packed layout pairs sub-sequences n1 = 2k, 2k+1; R2 <= 32: one lane per sub-sequence in the
+// first radix pass of a warp; PC * max(R1, R2) <= 256)
 BFFT_GEO(32, 4, 8, 16, 16)
 BFFT_GEO(36, 6, 6, 18, 16)
 BFFT_GEO(48, 6, 8, 12, 16)
@@ -325,6 +327,21 @@ BFFT_GEO(320, 20, 16, 16, 12)
 BFFT_GEO(360, 24, 15, 20, 10)
 BFFT_GEO(384, 24, 16, 16, 10)
 BFFT_GEO(400, 16, 25, 20, 10)
+// further common box sizes (radices 2/3/5/7), not individually tuned
+BFFT_GEO(100, 10, 10, 10, 16)
+BFFT_GEO(120, 8, 15, 12, 16)
+BFFT_GEO(144, 12, 12, 12, 16)
+BFFT_GEO(200, 20, 10, 10, 12)
+BFFT_GEO(216, 18, 12, 12, 12)
+BFFT_GEO(240, 16, 15, 20, 16)
+BFFT_GEO(300, 20, 15, 15, 12)
+BFFT_GEO(336, 24, 14, 12, 10)
+BFFT_GEO(420, 20, 21, 14, 12)
+BFFT_GEO(432, 16, 27, 12, 8)
+BFFT_GEO(448, 28, 16, 16, 8)
+BFFT_GEO(480, 20, 24, 16, 10)
+BFFT_GEO(500, 20, 25, 10, 10)
+BFFT_GEO(512, 16, 32, 16, 8)
 #undef BFFT_GEO
 
 } // namespace bfft

@@ -516,12 +516,15 @@ def test_exact_first_of_ties_displacement():
 
 
 def _prior(hi, ctfparam):
-    """prior term of calc_logpro in CTF mode (bioem_algorithm.h:49-56), double like the library's table"""
-    amp, pha, env = (float(x) for x in ctfparam[:3])
+    """prior term of calc_logpro in CTF mode (bioem_algorithm.h:49-56) with the library's (and the reference's)
+    arithmetic: products of floats are float products, the divisions run in double"""
+    f32 = np.float32
+    amp, pha, env = (f32(x) for x in ctfparam[:3])
     c = hi.cfg
-    return (env * env / 2. / c.sigmaPriorbctf / c.sigmaPriorbctf
-            - (pha - c.Priordefcent) * (pha - c.Priordefcent) / 2. / c.sigmaPriordefo / c.sigmaPriordefo
-            - (amp - c.Priorampcent) * (amp - c.Priorampcent) / 2. / c.sigmaPrioramp / c.sigmaPrioramp)
+    dp, da = pha - f32(c.Priordefcent), amp - f32(c.Priorampcent)
+    return (float(env * env) / 2. / float(f32(c.sigmaPriorbctf)) / float(f32(c.sigmaPriorbctf))
+            - float(dp * dp) / 2. / float(f32(c.sigmaPriordefo)) / float(f32(c.sigmaPriordefo))
+            - float(da * da) / 2. / float(f32(c.sigmaPrioramp)) / float(f32(c.sigmaPrioramp)))
 
 
 def test_exact_ties_between_ctfs_orientations_groups_and_launches(monkeypatch, setups):
