@@ -1025,7 +1025,7 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
       const float fmin = __uint_as_float((unsigned) (kmin >> 32));
       const float inv = __fdiv_rn(1.f, fmin);
       fminl = fmin;
-      lpf = (float) (p.acoef_d * log((double) fmin) + cpl.Bterm);
+      lpf = (float) __fma_rn(p.acoef_d, log((double) fmin), cpl.Bterm);
       lin = (int) (kmin & 0xffffffffu);
       bvv = s_wv[lane][wb];
 #pragma unroll 1
@@ -1067,7 +1067,7 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
       if (lc != 0x7fffffff)
       {
         tried = lc;
-        if ((float) (p.acoef_d * log((double) fc) + cpl.Bterm) == lpf)
+        if ((float) __fma_rn(p.acoef_d, log((double) fc), cpl.Bterm) == lpf)
         {
           lin = lc;
           tried = 0x7ffffffe; // done: nothing with a lower index is left
@@ -1342,8 +1342,10 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
               const float2 v = bfft::cscale(y[k2_of(j)], p.invNN);
               float2 f = __fmul2_rn(v, v);
               f = __fadd2_rn(make_float2(f_a, f_a), make_float2(-f.x, -f.y));
-              f = __fmul2_rn(make_float2(Nt, Nt), f);
-              f = __fadd2_rn(f, __fmul2_rn(make_float2(f_b, f_b), v));
+              // (one fused multiply-add, spelled out: ptxas contracts the separate multiply and add anyway, and
+              // exact_argmax_kernel must repeat this sequence bit for bit.  The reference's own build,
+              // -O3 -ffast-math -march=native, is free to contract here too, quirk Q7.)
+              f = __ffma2_rn(make_float2(Nt, Nt), f, __fmul2_rn(make_float2(f_b, f_b), v));
               f = __fadd2_rn(f, make_float2(-f_c, -f_c));
               f = __fadd2_rn(f, make_float2(-f_d, -f_d));
               const bool val = (vmask >> (t * NK + j)) & 1u;
@@ -1739,8 +1741,7 @@ __global__ void __launch_bounds__(128) exact_argmax_kernel(const RefineItem *__r
     // same sequence as the fused kernel's epilogue (value = correlation / N^2 was stored)
     float f = __fmul_rn(raw, raw);
     f = __fadd_rn(f_a, -f);
-    f = __fmul_rn(Nt, f);
-    f = __fadd_rn(f, __fmul_rn(f_b, raw));
+    f = __fmaf_rn(Nt, f, __fmul_rn(f_b, raw));
     f = __fadd_rn(f, -f_c);
     f = __fadd_rn(f, -f_d);
     return f;
@@ -1760,7 +1761,7 @@ __global__ void __launch_bounds__(128) exact_argmax_kernel(const RefineItem *__r
     __syncthreads();
   }
   fmin = s_f[0];
-  const float lpf = (float) (acoef * log((double) fmin) + cp.Bterm);
+  const float lpf = (float) __fma_rn(acoef, log((double) fmin), cp.Bterm);
   // logpro falls with firstele: whatever narrows to the same float lies within a few ulps of the minimum;
   // 2e-5 relative (~170 ulps) is a safe superset to run the double-precision log on
   const float fthr = fmin + fabsf(fmin) * 2e-5f;
@@ -1768,7 +1769,7 @@ __global__ void __launch_bounds__(128) exact_argmax_kernel(const RefineItem *__r
   for (int i = tid; i < n; i += 128)
   {
     const float f = firstele(v[i]);
-    if (f <= fthr && (float) (acoef * log((double) f) + cp.Bterm) == lpf)
+    if (f <= fthr && (float) __fma_rn(acoef, log((double) f), cp.Bterm) == lpf)
       best = min(best, i);
   }
   s_l[tid] = best;

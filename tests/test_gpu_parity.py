@@ -456,17 +456,22 @@ def test_out_of_frame_points_are_counted(setups):
     assert eng2.out_of_frame()[1] == 0
 
 
+def _fma32(a, b, c):
+    """float fma: the product of two floats is exact in double, one rounding to double, one to float"""
+    return (a.astype(np.float64) * np.float64(b) + c.astype(np.float64)).astype(np.float32)
+
+
 def _host_first_of_ties(eng, hi, parts_sum, o, c, m, prior):
     """The reference's rule applied on the host to the GPU's own correlation window of one likelihood:
-    firstele in FP32 in source order (bioem_algorithm.h:29-36), logpro in double, narrowed to float (:84),
-    first maximum in enumeration order (:96)."""
+    firstele in FP32 (bioem_algorithm.h:29-36; with the one multiply-add the kernel fuses), logpro in double,
+    narrowed to float (:84), first maximum in enumeration order (:96)."""
     f32 = np.float32
     v = eng.debug_correlation(o, c, m).astype(np.float32).ravel()
     _, sC, ssC = eng.debug_convolved(o, c)
     sR, ssR = parts_sum
     sC, ssC, sR, ssR = f32(sC), f32(ssC), f32(sR), f32(ssR)
     Nt = f32(hi.cfg.Ntotpi)
-    fe = Nt * (ssR * ssC - v * v) + (f32(2.0) * sR * sC) * v - (ssR * sC) * sC - (sR * sR) * ssC
+    fe = _fma32(ssR * ssC - v * v, Nt, (f32(2.0) * sR * sC) * v) - (ssR * sC) * sC - (sR * sR) * ssC
     assert fe.dtype == np.float32
     fl = ssC * Nt - sC * sC
     a = (3.0 - float(Nt)) * 0.5
@@ -477,19 +482,25 @@ def _host_first_of_ties(eng, hi, parts_sum, o, c, m, prior):
 
 def test_exact_first_of_ties_displacement():
     """Quirk Q10: logpro is narrowed to float before the comparison, so displacements tie exactly and the FIRST in
-    enumeration order must win.  A very smooth particle (a wide Gaussian blob) against a smooth model gives a flat
-    correlation peak at N = 224, where one float quantum of logpro spans several ulps of firstele: dozens of
-    displacements tie.  The library's arg-max must be the first of them -- checked against the rule applied on the
-    host to the GPU's own correlation window (so FFT rounding cannot blur the comparison)."""
+    enumeration order must win.  Particles that hardly correlate with the (smooth) projection make firstele
+    insensitive to the correlation value, so that whole regions of the window share one float logpro: a checkerboard
+    (zero sum, pure Nyquist frequency: |correlation| is the same at every displacement), a checkerboard plus a faint
+    blob, fine stripes plus faint noise.  The library's arg-max must be the first of the tying displacements --
+    checked against the rule applied on the host to the GPU's own correlation window (so FFT rounding cannot blur
+    the comparison)."""
     _need_gpu()
     cd = build_case("cfg2_slice", n_particles=2, n_orient=1)
     hi, parts = api.inputs_for_case(cd)
     n = hi.N
     g = np.arange(n, dtype=np.float64) - n / 2
-    blobs = []
-    for s, (cx, cy) in ((40.0, (3.0, -2.0)), (60.0, (-7.5, 5.5)), (25.0, (0.0, 0.0))):
-        b = np.exp(-((g[:, None] - cx) ** 2 + (g[None, :] - cy) ** 2) / (2 * s * s))
-        blobs.append(((b - b.mean()) / b.std()).astype(np.float32))
+    ii, jj = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+    checker = np.where((ii + jj) % 2 == 0, 1.0, -1.0)
+    blob = np.exp(-((g[:, None] - 3.0) ** 2 + (g[None, :] + 2.0) ** 2) / (2 * 30.0 ** 2))
+    rng = np.random.default_rng(5)
+    blobs = [checker.astype(np.float32),
+             (checker + 2e-3 * blob).astype(np.float32),
+             (np.where(ii % 2 == 0, 1.0, -1.0) + 1e-3 * rng.normal(size=(n, n))).astype(np.float32),
+             (checker * 3.0 + 0.5).astype(np.float32)]
     parts = np.ascontiguousarray(np.stack(blobs))
     one_ctf = (np.ascontiguousarray(hi.refCTF[5:6]), np.ascontiguousarray(hi.CtfParam[5:6]))
     e = _engine_with(hi, parts, ctf=one_ctf)
@@ -654,13 +665,17 @@ def test_mrc_ingest_on_device_matches_host_reader(setups):
     assert a.tobytes() == b.tobytes()
 
 
-@pytest.mark.parametrize("n", [32, 36, 48, 64, 96, 128, 160, 192, 224, 256, 288, 320, 360, 384, 400])
-def test_every_instantiated_image_edge_matches_oracle(n):
+@pytest.mark.parametrize("n,maxd", [(n, min(10, n // 4)) for n in (32, 36, 48, 64, 96, 100, 120, 128, 144, 160, 192, 200, 216, 224, 240,
+                                                                    256, 288, 300, 320, 336, 360, 384, 400, 420, 432, 448, 480,
+                                                                    500, 512)]
+                         + [(200, 40), (300, 40), (448, 40), (512, 40), (100, 7)])
+def test_every_instantiated_image_edge_matches_oracle(n, maxd):
     """One tiny run per image edge the kernels are instantiated for (mixed radices 2/3/5/7,
-    one or two CTAs per SM, 8-12 warps): log P and arg-max against the oracle."""
+    one or two CTAs per SM, 4-12 warps): log P and arg-max against the oracle; the largest edges also with the
+    production window DISPLACE_CENTER 40 (shared-memory fit)."""
     _need_gpu()
     from bioem_b200.cases import CFG1_CTF, Case
-    case = Case(f"edge{n}", n, 1.5, 40, 2, 576, 2, CFG1_CTF, min(10, n // 4), 1,
+    case = Case(f"edge{n}", n, 1.5, 40, 2, 576, 2, CFG1_CTF, maxd, 1,
                 model_sigma=n / 12.0, model_rmax=n / 4.0, particle_format="mrc")
     cd = build_case(case)
     hi, parts = api.inputs_for_case(cd)

@@ -28,15 +28,15 @@ def test_library_exports_every_declared_symbol():
 
 def test_supported_sizes():
     L = api.lib()
-    for n in (32, 36, 64, 128, 224, 360):
+    for n in (32, 36, 64, 100, 128, 200, 224, 240, 300, 360, 448, 512):
         assert L.bioem_b200_supported_size(n) == 1
-    for n in (31, 100, 225, 1024):
+    for n in (31, 102, 225, 1024):
         assert L.bioem_b200_supported_size(n) == 0
 
 
 def test_create_fails_loudly_without_device_or_with_bad_config():
     L = api.lib()
-    cfg = api.Config(100, 4, 1, 0, 0, 1, 0, 0, 1.0, 1e4, 1.0, 1, 1, 1, 1, 0)
+    cfg = api.Config(102, 4, 1, 0, 0, 1, 0, 0, 1.0, 102.0 * 102.0, 1.0, 1, 1, 1, 1, 0)
     h = C.c_void_p()
     assert L.bioem_b200_create(C.byref(cfg), 0, C.byref(h)) == 1  # unsupported size
     assert b"NUMBER_PIXELS" in L.bioem_b200_last_error()
