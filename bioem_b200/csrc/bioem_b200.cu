@@ -106,7 +106,7 @@ struct bioem_b200_context
   float2 *d_tw_inv = nullptr, *d_tw_fwd = nullptr;
   unsigned char *d_wtab = nullptr;
   // batch buffers
-  int OB = 0, OG = 1, nbands = 1, band_rows = 0;
+  int OB = 0, OG = 1, nbands = 1, band_rows = 0, proj_threads = 256;
   float *d_proj = nullptr;
   double *d_tempden = nullptr;
   float2 *d_scratch = nullptr;
@@ -814,14 +814,27 @@ static int ensure_batch(bioem_b200_context *h)
   if (env_pos("BIOEM_B200_OG"))
     og = (int) env_pos("BIOEM_B200_OG");
   h->OG = og;
-  // bands of image rows per projection CTA: small bands = many CTAs (an orientation batch is only
-  // ~15 images), at the price of every warp skipping more model points that miss its rows
+  // Bands of image rows per projection CTA.  Every warp of a band walks the model points that touch the band IN
+  // ORDER (a serial chain), so what hides its latency is the number of resident warps: aim at >= 4 x 148 CTAs per
+  // launch, within 24 KB of band per CTA.  Large batches (cfg 2: 165 orientations) reach that with 9 bands of 26
+  // rows and 8 warps; small batches of a big model (cfg 4: 8 orientations of 110,592 voxels) get 90 bands of 4 rows
+  // with one row per warp -- 3.7 ms per orientation with the 22 bands of 17 rows this used to launch.
   size_t band_budget = 24 * 1024;
   if (env_pos("BIOEM_B200_BAND_KB"))
     band_budget = (size_t) env_pos("BIOEM_B200_BAND_KB") * 1024;
-  h->nbands = (int) (((size_t) N * N * 4 + band_budget - 1) / band_budget);
+  const int by_budget = (int) (((size_t) N * N * 4 + band_budget - 1) / band_budget);
+  const int by_ctas = (int) std::min<long>((4 * 148 + h->OB - 1) / h->OB, N);
+  h->nbands = std::max(1, std::max(by_budget, by_ctas));
   h->band_rows = (N + h->nbands - 1) / h->nbands;
+  if (h->band_rows < 8)
+  { // one row per warp, a power of two of warps (the kernel splits its point tiles evenly over the warps)
+    int r = 1;
+    while (2 * r <= h->band_rows)
+      r *= 2;
+    h->band_rows = r;
+  }
   h->nbands = (N + h->band_rows - 1) / h->band_rows;
+  h->proj_threads = 32 * std::min(8, h->band_rows);
   const int OB = h->OB;
   h->OB = 0; // a failed allocation below leaves "no batch buffers" behind, not a half-built set
   RC(dev_realloc(h, h->d_proj, (size_t) N * N * OB));
@@ -894,7 +907,7 @@ static int run_front(bioem_b200_context *h, int o0, int OBcur, const float4 *ang
   // the attribute belongs to the function, not to this handle: other handles (other image sizes)
   // may have changed it since, so it is set at every launch
   CU(cudaFuncSetAttribute(project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ((size_t) h->band_rows * N * 4)));
-  project_kernel<<<pg, 256, (size_t) h->band_rows * N * 4, h->stream>>>(pp);
+  project_kernel<<<pg, h->proj_threads, (size_t) h->band_rows * N * 4, h->stream>>>(pp);
   CU(cudaGetLastError());
   CU(do_fft2d(N, h->d_proj, h->d_tempden, h->nbands, h->NormDen, h->d_tw_fwd, h->d_scratch, h->d_projfft, OBcur, h->stream));
   CU(do_conv(N, h->d_projfft, h->d_ctf, h->d_prior, h->d_conv, h->d_cpar, h->C, OBcur, h->cfg.Ntotpi, h->stream, sel, nsel));

@@ -232,51 +232,68 @@ __global__ void __launch_bounds__(256) project_kernel(ProjParams p)
   const float half = __fdiv_rn((float) N, 2.0f);
   float td = 0.f; // per-lane share of tempden
   int nskip = 0;
-  // Model points are taken in tiles: the CTA's threads rotate a tile once (pixel the point lands on,
-  // radius, density -> shared memory), then every warp walks the tile IN ORDER and adds the points
-  // that touch its rows.  (Rotating inside the walk made all warps of all bands repeat it.)
+  // Model points are taken in tiles of PT.  Phase A: warp w rotates the points [w*SEG, (w+1)*SEG) of the tile, 32
+  // consecutive points per trip, and keeps -- in order, compacted with a ballot -- only those whose footprint
+  // touches THIS CTA's band of rows (s_pt[w*SEG ..], s_cnt[w]); with a 48^3 voxel model that is ~3 % of the
+  // 110,592 points.  Phase B: every warp walks the kept points of all segments in order, 32 at a time: one ballot
+  // tells which of them touch the warp's own rows, and only those are rasterised, lowest index first -- the order
+  // of the reference's loop over the model points, so every pixel receives its contributions in model order
+  // (deterministic, no atomics).
   constexpr int PT = 1024;
-  __shared__ int4 s_pt[PT]; // i, j, radius bits, density bits; i = INT_MIN: out of frame
+  __shared__ int4 s_pt[PT]; // i, j, radius bits, density bits
+  __shared__ int s_cnt[8];
+  const int SEG = PT / nwarps; // nwarps is 1, 2, 4 or 8
   for (int n0 = 0; n0 < p.A; n0 += PT)
   {
-    const int nt = min(PT, p.A - n0);
-    for (int k = tid; k < nt; k += blockDim.x)
+    int cnt = 0;
+    for (int kk = 0; kk < SEG; kk += 32)
     {
-      const float4 pt = __ldg(&p.xyzr[n0 + k]);
-      const float den = __ldg(&p.dens[n0 + k]);
-      const float rx = __fadd_rn(__fadd_rn(__fadd_rn(0.f, __fmul_rn(m00, pt.x)), __fmul_rn(m01, pt.y)), __fmul_rn(m02, pt.z));
-      const float ry = __fadd_rn(__fadd_rn(__fadd_rn(0.f, __fmul_rn(m10, pt.x)), __fmul_rn(m11, pt.y)), __fmul_rn(m12, pt.z));
-      int i = (int) floorf(__fadd_rn(__fadd_rn(__fdiv_rn(rx, px), half), 0.5f));
-      int j = (int) floorf(__fadd_rn(__fadd_rn(__fdiv_rn(ry, px), half), 0.5f));
-      const float radius = pt.w;
-      bool skip;
-      if (radius <= px)
-        skip = i < 0 || j < 0 || i >= N || j >= N;
-      else
+      const int k = warp * SEG + kk + lane;
+      bool keep = false, out = false;
+      int4 e = make_int4(0, 0, 0, 0);
+      if (n0 + k < p.A)
       {
-        i -= p.shiftX;
-        j -= p.shiftY;
-        const int irad = (int) __fdiv_rn(radius, px) + 1;
-        skip = i < irad || j < irad || i >= N - irad || j >= N - irad;
-      }
-      s_pt[k] = make_int4(skip ? (int) 0x80000000 : i, j, __float_as_int(radius), __float_as_int(den));
-    }
-    __syncthreads();
-    // Each warp looks at 32 points of the tile at once: one ballot tells which of them touch the warp's
-    // rows, and only those are rasterised, lowest index first -- the order of the reference's loop over the
-    // model points, so every pixel still receives its contributions in model order.  (Walking the tile point
-    // by point cost every warp of every band ~10 instructions per point that misses its rows: 2.7 ms per
-    // orientation with the 110,592 voxels of a 48^3 MRC model.)
-    for (int k0 = 0; k0 < nt; k0 += 32)
-    {
-      int4 e = make_int4((int) 0x80000000, 0, 0, 0);
-      bool hit = false, out = false;
-      if (k0 + lane < nt)
-      {
-        e = s_pt[k0 + lane];
-        out = e.x == (int) 0x80000000;
-        if (!out)
+        const float4 pt = __ldg(&p.xyzr[n0 + k]);
+        const float den = __ldg(&p.dens[n0 + k]);
+        const float rx = __fadd_rn(__fadd_rn(__fadd_rn(0.f, __fmul_rn(m00, pt.x)), __fmul_rn(m01, pt.y)), __fmul_rn(m02, pt.z));
+        const float ry = __fadd_rn(__fadd_rn(__fadd_rn(0.f, __fmul_rn(m10, pt.x)), __fmul_rn(m11, pt.y)), __fmul_rn(m12, pt.z));
+        int i = (int) floorf(__fadd_rn(__fadd_rn(__fdiv_rn(rx, px), half), 0.5f));
+        int j = (int) floorf(__fadd_rn(__fadd_rn(__fdiv_rn(ry, px), half), 0.5f));
+        const float radius = pt.w;
+        if (radius <= px)
         {
+          out = i < 0 || j < 0 || i >= N || j >= N;
+          keep = !out && i >= r0 && i < r1;
+        }
+        else
+        {
+          i -= p.shiftX;
+          j -= p.shiftY;
+          const int irad = (int) __fdiv_rn(radius, px) + 1;
+          out = i < irad || j < irad || i >= N - irad || j >= N - irad;
+          keep = !out && !(i + irad < r0 || i - irad >= r1);
+        }
+        e = make_int4(i, j, __float_as_int(radius), __float_as_int(den));
+      }
+      nskip += __popc(__ballot_sync(0xffffffffu, out));
+      const unsigned km = __ballot_sync(0xffffffffu, keep);
+      if (keep)
+        s_pt[warp * SEG + cnt + __popc(km & ((1u << lane) - 1u))] = e;
+      cnt += __popc(km);
+    }
+    if (lane == 0)
+      s_cnt[warp] = cnt;
+    __syncthreads();
+    for (int ws = 0; ws < nwarps; ws++)
+    {
+      const int nt = s_cnt[ws];
+      for (int k0 = 0; k0 < nt; k0 += 32)
+      {
+        int4 e = make_int4(0, 0, 0, 0);
+        bool hit = false;
+        if (k0 + lane < nt)
+        {
+          e = s_pt[ws * SEG + k0 + lane];
           const float radius = __int_as_float(e.z);
           if (radius <= px)
             hit = e.x >= wr0 && e.x < wr1;
@@ -286,50 +303,51 @@ __global__ void __launch_bounds__(256) project_kernel(ProjParams p)
             hit = !(e.x + irad < wr0 || e.x - irad >= wr1);
           }
         }
-      }
-      nskip += __popc(__ballot_sync(0xffffffffu, out));
-      unsigned todo = __ballot_sync(0xffffffffu, hit);
-      while (todo)
-      {
-        const int src = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const int i = __shfl_sync(0xffffffffu, e.x, src), j = __shfl_sync(0xffffffffu, e.y, src);
-        const float radius = __int_as_float(__shfl_sync(0xffffffffu, e.z, src));
-        const float den = __int_as_float(__shfl_sync(0xffffffffu, e.w, src));
-        if (radius <= px)
+        unsigned todo = __ballot_sync(0xffffffffu, hit);
+        while (todo)
         {
-          if (lane == 0)
+          const int src = __ffs(todo) - 1;
+          todo &= todo - 1;
+          const int i = __shfl_sync(0xffffffffu, e.x, src), j = __shfl_sync(0xffffffffu, e.y, src);
+          const float radius = __int_as_float(__shfl_sync(0xffffffffu, e.z, src));
+          const float den = __int_as_float(__shfl_sync(0xffffffffu, e.w, src));
+          if (radius <= px)
           {
-            band[(i - r0) * N + j] = __fadd_rn(band[(i - r0) * N + j], den);
-            td = __fadd_rn(td, den);
-          }
-        }
-        else
-        {
-          const int irad = (int) __fdiv_rn(radius, px) + 1;
-          const float rad2 = __fmul_rn(radius, radius);
-          const int S = 2 * irad + 1;
-          const double denom = 4 * 3.14159265358979323846 * (double) radius * (double) rad2;
-          for (int idx = lane; idx < S * S; idx += 32)
-          {
-            const int di = idx / S - irad, dj = idx % S - irad;
-            const int ii = i + di, jj = j + dj;
-            if (ii < wr0 || ii >= wr1)
-              continue;
-            // dist = ((float)(di)*di + dj*dj) * px * px
-            const float dist = __fmul_rn(__fmul_rn(__fadd_rn(__fmul_rn((float) di, (float) di), (float) (dj * dj)), px), px);
-            if (dist < rad2)
+            if (lane == 0)
             {
-              const float num = __fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(px, px), 2.f), sqrtf(__fsub_rn(rad2, dist))), den), 3.f);
-              const double w = (double) num / denom;
-              float *px_ = &band[(ii - r0) * N + jj];
-              *px_ = (float) ((double) *px_ + w);
-              td = (float) ((double) td + w);
+              band[(i - r0) * N + j] = __fadd_rn(band[(i - r0) * N + j], den);
+              td = __fadd_rn(td, den);
             }
           }
+          else
+          {
+            const int irad = (int) __fdiv_rn(radius, px) + 1;
+            const float rad2 = __fmul_rn(radius, radius);
+            const int S = 2 * irad + 1;
+            const double denom = 4 * 3.14159265358979323846 * (double) radius * (double) rad2;
+            // lanes cover only the footprint rows this warp owns (one trip for the usual 7 x 7 footprint of a
+            // voxel model and a warp of one to four rows), in the reference's ii-outer / jj-inner order
+            const int d_lo = max(-irad, wr0 - i), d_hi = min(irad, wr1 - 1 - i);
+            const int cells = (d_hi - d_lo + 1) * S;
+            for (int idx = lane; idx < cells; idx += 32)
+            {
+              const int di = idx / S + d_lo, dj = idx % S - irad;
+              const int ii = i + di, jj = j + dj;
+              // dist = ((float)(di)*di + dj*dj) * px * px
+              const float dist = __fmul_rn(__fmul_rn(__fadd_rn(__fmul_rn((float) di, (float) di), (float) (dj * dj)), px), px);
+              if (dist < rad2)
+              {
+                const float num = __fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(px, px), 2.f), sqrtf(__fsub_rn(rad2, dist))), den), 3.f);
+                const double w = (double) num / denom;
+                float *px_ = &band[(ii - r0) * N + jj];
+                *px_ = (float) ((double) *px_ + w);
+                td = (float) ((double) td + w);
+              }
+            }
+          }
+          // the next point may touch the same pixels from other lanes: order the read-modify-writes
+          __syncwarp();
         }
-        // the next point may touch the same pixels from other lanes: order the read-modify-writes
-        __syncwarp();
       }
     }
     __syncthreads();
@@ -341,6 +359,8 @@ __global__ void __launch_bounds__(256) project_kernel(ProjParams p)
   // deterministic reduction of the tempden shares: lanes then warps, fixed order
   __shared__ float s_td[256];
   s_td[tid] = td;
+  if (lane == 0)
+    s_cnt[warp] = nskip; // out-of-frame points of the segments this warp rotated
   __syncthreads();
   if (tid == 0)
   {
@@ -349,7 +369,12 @@ __global__ void __launch_bounds__(256) project_kernel(ProjParams p)
       t += (double) s_td[k];
     p.tempden[(size_t) ob * p.nbands + b] = t;
     if (p.skipped && b == 0)
-      p.skipped[p.o_base + ob] = nskip; // every thread has counted every out-of-frame point of the model
+    {
+      int ns = 0;
+      for (int w = 0; w < nwarps; w++)
+        ns += s_cnt[w];
+      p.skipped[p.o_base + ob] = ns; // every band rotates the whole model: band 0 reports
+    }
   }
 }
 
@@ -748,9 +773,17 @@ template <int N> struct LikGeo
   // output groups, which buys two more warps at N = 320 / 360 and the 24 x 16 split at N = 384.
   static constexpr bool COMPACT = N > 224;
   __host__ __device__ static constexpr int rows(int W, int nwp) { return COMPACT ? nwp : nk(W) * L::R1; }
+  // BIOEM_TMA (measured variant, profiles/r02_tma_variant.md): one staging slot per warp for the conv and the
+  // particle chunk of its next column task, filled by cp.async.bulk
+  static constexpr int CHUNK4 = (L::R1 / 2) * KC * L::R2; // float4 per operand chunk (contiguous in the packed layout)
+#ifdef BIOEM_TMA
+  static constexpr size_t OPS_BYTES = 2 * (size_t) CHUNK4 * 16;
+#else
+  static constexpr size_t OPS_BYTES = 0;
+#endif
   __host__ __device__ static constexpr size_t dyn_bytes(int W, int nwarp, int nwp)
   {
-    return ((size_t) rows(W, nwp) * YS + (size_t) nwarp * EW) * sizeof(float2) + ((N + 15) & ~15) + 256;
+    return ((size_t) rows(W, nwp) * YS + (size_t) nwarp * EW) * sizeof(float2) + ((N + 15) & ~15) + 256 + nwarp * OPS_BYTES;
   }
 };
 template <int N> __host__ __device__ constexpr int lik_window_groups(int maxD);
@@ -793,7 +826,11 @@ template <int N> struct LikSmem
   static constexpr int LNT = 32 * NWARP; // threads per CTA
   // registers per thread: two CTAs per SM up to N = 224 (registers are granted to a CTA in units
   // of 4 warps, so 7 warps cost as many as 8), one CTA per SM above
+#ifdef BIOEM_MAXREG
+  static constexpr int MAXREG = BIOEM_MAXREG;
+#else
   static constexpr int MAXREG = N <= 224 ? 128 : (65536 / (32 * ((NWARP + 3) / 4 * 4))) / 8 * 8 > 255 ? 255 : (65536 / (32 * ((NWARP + 3) / 4 * 4))) / 8 * 8;
+#endif
   static constexpr int KC = G::KC, CS = G::CS, ES = G::ES, YS = G::YS, EW = G::EW;
   static constexpr bool WIDE = G::WIDE;
   __host__ __device__ static constexpr int nk(int W) { return G::nk(W); }
@@ -897,6 +934,12 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
   float2 *Eall = Y + (size_t) SM::G::rows(W, p.nwp) * YS;
   unsigned char *WT = reinterpret_cast<unsigned char *>(Eall + (size_t) NWARP * SM::EW);
   unsigned char *RS = WT + ((N + 15) & ~15);
+#ifdef BIOEM_TMA
+  constexpr int CHUNK4 = SM::G::CHUNK4;
+  constexpr unsigned CHUNKB = CHUNK4 * 16;
+  float4 *OPS = reinterpret_cast<float4 *>(RS + 256) + (size_t) (threadIdx.x >> 5) * 2 * CHUNK4; // [conv chunk][particle chunk]
+  __shared__ unsigned long long s_tbar[NWARP];
+#endif
   // ring of likelihoods waiting for their bookkeeping, one entry per warp and likelihood:
   // minimum key (firstele bits << 32 | enumeration index), runner-up candidate (enumeration index
   // << 32 | firstele bits), sum of exp relative to the warp minimum, correlation value at the minimum
@@ -932,6 +975,13 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
   }
   const unsigned mbar_addr = (unsigned) __cvta_generic_to_shared(&s_mbar);
   unsigned mbar_parity = 0;
+#ifdef BIOEM_TMA
+  const unsigned tbar_addr = (unsigned) __cvta_generic_to_shared(&s_tbar[warp]);
+  const unsigned ops_addr = (unsigned) __cvta_generic_to_shared(OPS);
+  unsigned tbar_parity = 0;
+  if (lane == 0)
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tbar_addr), "r"(1) : "memory");
+#endif
   if (tid == 0)
   {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar_addr), "r"(NWARP) : "memory");
@@ -991,6 +1041,10 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
   auto expa1p = [&](float t) { return ex2_ftz(t * fmaf(t, fmaf(t, c3, c2), c1)); };
 
   const float4 *ref = p.refs + (size_t) m * L::MAP4;
+  // first column chunk of this warp.  Chunk 0 (which also carries the Nyquist column: half as many
+  // loads and multiplies again) goes to the last warp, which has the fewest row tasks: its first
+  // radix pass runs in that warp's slack before the closing barrier.
+  const int ch0 = (warp + 1) % NWARP;
   const float sR = p.sumRef[m], ssR = p.sumsqRef[m];
   const float Nt = p.Ntotpi;
   int slot = 0; // likelihoods in the ring (uniform over the CTA)
@@ -1123,8 +1177,72 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
   //   col2: radix-R2 (pruned) from the tile -> row slots of Y
   // (FIRST: chunk 0, which also carries the Nyquist column -- a separate instance, so that the
   // other 55 chunks do not pay the register moves that merge the two paths)
-  auto col1_ = [&](int ch, const float4 *conv, auto first_) {
+#ifdef BIOEM_TMA
+  // one elected lane asks the copy engine for the conv and the particle chunk of a column task: two contiguous
+  // 3.5 KB blocks of the packed layout -> this warp's staging slot, completion counted on the warp's mbarrier
+  auto tma_issue = [&](int ch, const float4 *conv) {
+    if (lane == 0)
+    {
+      const float4 *gc = conv + (size_t) ch * CHUNK4, *gr = ref + (size_t) ch * CHUNK4;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tbar_addr), "r"(2u * CHUNKB) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(ops_addr),
+                   "l"(gc), "r"(CHUNKB), "r"(tbar_addr)
+                   : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(ops_addr + CHUNKB),
+                   "l"(gr), "r"(CHUNKB), "r"(tbar_addr)
+                   : "memory");
+    }
+  };
+#endif
+  // (more: another likelihood follows the one conv belongs to -- only the staging variant needs to know)
+  auto col1_ = [&](int ch, const float4 *conv, bool more, auto first_) {
     constexpr bool FIRST = decltype(first_)::value;
+#ifdef BIOEM_TMA
+    {
+      unsigned done;
+      do
+      {
+        // (with a suspend-time hint, like the closing barrier: without it the waiting warps poll through the issue
+        // slots of the others -- +13 % warp instructions per likelihood, measured)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2, %3;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(tbar_addr), "r"(tbar_parity), "r"(0x989680u)
+                     : "memory");
+      } while (!done);
+      tbar_parity ^= 1u;
+    }
+    float2 x[R1];
+    if (a_act)
+    {
+#pragma unroll
+      for (int n1p = 0; n1p < R1 / 2; n1p++)
+      {
+        const float4 v = OPS[n1p * KC * R2 + lane];
+        const float4 r = OPS[CHUNK4 + n1p * KC * R2 + lane];
+        x[2 * n1p] = bfft::cmulc(make_float2(v.x, v.y), make_float2(r.x, r.y));
+        x[2 * n1p + 1] = bfft::cmulc(make_float2(v.z, v.w), make_float2(r.z, r.w));
+      }
+    }
+    // the slot has been consumed (its values are in x): hand it back to the copy engine for this warp's next task
+    __syncwarp();
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    {
+      int nch = ch + NWARP;
+      const float4 *nconv = conv;
+      bool have = true;
+      if (nch >= NCH)
+      {
+        nch = ch0;
+        nconv = conv + L::MAP4;
+        have = more;
+      }
+      if (have)
+        tma_issue(nch, nconv);
+    }
+    if (a_act)
+    {
+#else
     if (a_act)
     {
       float2 x[R1];
@@ -1137,6 +1255,7 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
         x[2 * n1p] = bfft::cmulc(make_float2(v.x, v.y), make_float2(r.x, r.y));
         x[2 * n1p + 1] = bfft::cmulc(make_float2(v.z, v.w), make_float2(r.z, r.w));
       }
+#endif
       if constexpr (FIRST)
       {
         if (a_c == 0)
@@ -1162,11 +1281,11 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
     }
     __syncwarp();
   };
-  auto col1 = [&](int ch, const float4 *conv) {
+  auto col1 = [&](int ch, const float4 *conv, bool more) {
     if (ch == 0)
-      col1_(ch, conv, std::true_type{});
+      col1_(ch, conv, more, std::true_type{});
     else
-      col1_(ch, conv, std::false_type{});
+      col1_(ch, conv, more, std::false_type{});
   };
   auto col2 = [&](int ch) {
 #pragma unroll
@@ -1226,11 +1345,11 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
   // pass 1 of this warp's first column chunk was already run behind the closing barrier of the
   // previous likelihood
   bool pre_done = false;
-  // first column chunk of this warp.  Chunk 0 (which also carries the Nyquist column: half as many
-  // loads and multiplies again) goes to the last warp, which has the fewest row tasks: its first
-  // radix pass runs in that warp's slack before the closing barrier.
-  const int ch0 = (warp + 1) % NWARP;
 
+#ifdef BIOEM_TMA
+  if (o_lo < o_hi)
+    tma_issue(ch0, p.convs + (size_t) o_lo * p.C * L::MAP4);
+#endif
   for (int ol = o_lo; ol < o_hi; ol++)
   {
     if (tid == 0)
@@ -1255,7 +1374,7 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
       for (int ch = ch0; ch < NCH; ch += NWARP)
       {
         if (!(pre_done && ch == ch0))
-          col1(ch, conv);
+          col1(ch, conv, oc + 1 < o_hi * p.C);
         col2(ch);
       }
       pre_done = false;
@@ -1449,7 +1568,7 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
         asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(mbar_addr) : "memory");
       if (ch0 < NCH && oc + 1 < o_hi * p.C)
       {
-        col1(ch0, conv + L::MAP4); // the next conv spectrum of the batch follows this one
+        col1(ch0, conv + L::MAP4, oc + 2 < o_hi * p.C); // the next conv spectrum of the batch follows this one
         pre_done = true;
       }
       {
