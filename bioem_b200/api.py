@@ -53,7 +53,7 @@ EXPORTS = [
     "bioem_b200_run", "bioem_b200_synchronize", "bioem_b200_download", "bioem_b200_download_top_angles",
     "bioem_b200_partial_bytes", "bioem_b200_export_partial", "bioem_b200_import_partials",
     "bioem_b200_merge_host", "bioem_b200_merge_peers", "bioem_b200_merge_top_angles_peers",
-    "bioem_b200_nccl_unique_id", "bioem_b200_nccl_init", "bioem_b200_nccl_attach", "bioem_b200_merge_nccl",
+    "bioem_b200_nccl_unique_id", "bioem_b200_nccl_init", "bioem_b200_nccl_attach", "bioem_b200_nccl_comm", "bioem_b200_merge_nccl",
     "bioem_b200_top_angles_nccl", "bioem_b200_set_kernel_timing", "bioem_b200_out_of_frame",
     "bioem_b200_exact_argmax_info", "bioem_b200_stream", "bioem_b200_device_angles", "bioem_b200_stats",
     "bioem_b200_kernel_time", "bioem_b200_debug_projection", "bioem_b200_debug_convolved",
@@ -111,6 +111,8 @@ def lib():
     L.bioem_b200_nccl_unique_id.argtypes = [vp]
     L.bioem_b200_nccl_init.argtypes = [vp, C.c_int, C.c_int, vp]
     L.bioem_b200_nccl_attach.argtypes = [vp, vp]
+    L.bioem_b200_nccl_comm.argtypes = [vp]
+    L.bioem_b200_nccl_comm.restype = vp
     L.bioem_b200_merge_nccl.argtypes = [vp]
     L.bioem_b200_top_angles_nccl.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp]
     L.bioem_b200_set_kernel_timing.argtypes = [vp, C.c_int]
@@ -354,6 +356,13 @@ class Engine:
         (the launcher broadcasts it: plumbing)."""
         buf = C.create_string_buffer(bytes(unique_id), 128)
         _chk(lib().bioem_b200_nccl_init(self._h, int(n_ranks), int(rank), buf), "nccl_init")
+
+    def nccl_comm(self) -> int:
+        return int(lib().bioem_b200_nccl_comm(self._h) or 0)
+
+    def nccl_attach(self, comm: int):
+        """Use an existing ncclComm_t (e.g. another Engine's nccl_comm() on the same device); not owned."""
+        _chk(lib().bioem_b200_nccl_attach(self._h, C.c_void_p(comm)), "nccl_attach")
 
     def merge_nccl(self):
         """One NCCL all-gather of the per-image partials + the fold in rank order, on the handle's stream."""

@@ -1375,6 +1375,8 @@ int bioem_b200_nccl_attach(bioem_b200_handle h, void *ncclComm)
   return BIOEM_B200_OK;
 }
 
+void *bioem_b200_nccl_comm(bioem_b200_handle h) { return h ? h->nccl_comm : nullptr; }
+
 int bioem_b200_merge_nccl(bioem_b200_handle h)
 {
   if (!h || !h->nccl_comm)

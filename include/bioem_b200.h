@@ -187,6 +187,9 @@ int bioem_b200_merge_top_angles_peers(bioem_b200_handle *handles, const int *oBe
 int bioem_b200_nccl_unique_id(void *id128);
 int bioem_b200_nccl_init(bioem_b200_handle h, int nRanks, int rank, const void *id128);
 int bioem_b200_nccl_attach(bioem_b200_handle h, void *ncclComm);
+/* the handle's communicator (an ncclComm_t; NULL if none): lets further handles of the same process and device
+ * share it through bioem_b200_nccl_attach instead of building their own (it stays owned by this handle) */
+void *bioem_b200_nccl_comm(bioem_b200_handle h);
 /* one ncclAllGather of the per-image partials (48 bytes per image and rank) on the handle's stream,
  * followed in stream order by the fold in rank order: every rank ends up with the merged state.
  * Collective: every rank of the communicator must call it.  Asynchronous like run(). */

@@ -80,8 +80,21 @@ def post(label, rnd):
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
     tj = os.path.join(prof, "ncu_traffic.json")
     t = json.load(open(tj)) if os.path.exists(tj) else {}
+    def pct(k):
+        try:
+            return round(float(d[k]), 1)
+        except Exception:
+            return None
+    sectors = float(d.get("lts__t_sectors_srcunit_tex_op_read.sum", "nan"))
     t["likelihood_kernel<224>"] = {
         "dram_bytes_per_likelihood": round((rd * scale[ur] + wr * scale[uw]) / NLIK, 1),
+        # what actually binds (the roofline "frac" of bench.py is the algorithmic ratio of SURVEY 8d, not DRAM utilisation)
+        "dram_pct_of_peak": pct("dram__throughput.avg.pct_of_peak_sustained_elapsed"),
+        "lsu_data_pipe_pct": pct("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"),
+        "fma_pipe_pct": pct("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
+        "issue_slot_pct": pct("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+        "l2_to_sm_bytes_per_likelihood": round(32.0 * sectors / NLIK, 1) if sectors == sectors else None,
+        "capture": f"profiles/{rnd}_likelihood_kernel_{label}_ncu.txt",
         "source": f"ncu --set full, profiles/{rnd}_likelihood_kernel_{label}_ncu.txt: dram__bytes_read.sum + dram__bytes_write.sum of one "
                   f"launch of {NLIK} likelihoods"}
     json.dump(t, open(tj, "w"), indent=1)
