@@ -26,6 +26,7 @@ from __future__ import annotations
 import argparse
 import json
 import os
+import re
 import subprocess
 import sys
 import tempfile
@@ -380,6 +381,25 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def _mkl_lib() -> str:
+    """PyTorch's libtorch_cpu.so is linked against Intel oneMKL and exports its DFTI entry points: the FFTW-API shim of
+    the reference build (oracle/fftw_shim) binds them at run time when BIOEM_FFT_MKL_LIB names the file."""
+    if os.environ.get("BIOEM_REF_FFT", "mkl") != "mkl":
+        return ""
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("torch")
+        path = os.path.join(os.path.dirname(spec.origin), "lib", "libtorch_cpu.so")
+        return path if os.path.exists(path) else ""
+    except Exception:
+        return ""
+
+
+FFT_LABEL = {"mkl": "Intel oneMKL DFTI (the copy PyTorch bundles, bound at run time by oracle/fftw_shim; FFTW 3 is not in the image)",
+             "builtin": "built-in engine of the FFTW-API shim (oracle/fft_core.hpp, builder code; FFTW 3 is not in the image)"}
+_LAST_FFT = {"engine": "builtin"}
+
+
 def _ref_slice(workload: str, n_orient: int, n_part: int, workdir: str, threads: int, stages: dict | None = None):
     """Run oracle/_ref/bioEM_ref on the first n_orient orientations x all CTFs x n_part particles
     of the workload; returns (likelihoods, seconds of the reference's own run() timer)."""
@@ -387,7 +407,7 @@ def _ref_slice(workload: str, n_orient: int, n_part: int, workdir: str, threads:
     cname, _, _ = WORKLOADS[workload]
     cd = build_case(cname, workdir, n_particles=n_part, n_orient=n_orient)
     refbin = os.path.join(ROOT, "oracle", "_ref", "bioEM_ref")
-    env = {**os.environ, "OMP_NUM_THREADS": str(threads)}
+    env = {**os.environ, "OMP_NUM_THREADS": str(threads), "BIOEM_FFT_MKL_LIB": _mkl_lib()}
     env.pop("GPU", None)
     if stages is not None:
         env["BIOEM_DEBUG_OUTPUT"] = "1"  # the reference's own stage timers (timer.cpp:156-165)
@@ -396,11 +416,14 @@ def _ref_slice(workload: str, n_orient: int, n_part: int, workdir: str, threads:
         raise RuntimeError("reference binary failed: " + r.stdout[-500:] + r.stderr[-500:])
     sec = None
     for ln in r.stdout.splitlines():
+        if ln.startswith("FFT engine:"):
+            _LAST_FFT["engine"] = "mkl" if "oneMKL" in ln else "builtin"
         if "The code ran for" in ln:
             sec = float(ln.split("for")[1].split("seconds")[0])
-        if stages is not None and ln.startswith("SUMMARY -> ") and "Total" in ln:
-            name = ln[len("SUMMARY -> "):].split(":")[0].strip()
-            stages[name] = float(ln.split("Total")[1].split("sec")[0])
+        if stages is not None:
+            mm = re.match(r"SUMMARY -> (.*?): Total ([0-9.eE+-]+) sec", ln)
+            if mm:
+                stages[mm.group(1).strip()] = float(mm.group(2))
     return cd.case.likelihoods, sec
 
 
@@ -430,11 +453,12 @@ def cpu_baseline(workload: str, budget_s: float = 15.0) -> dict:
             stages = {}
     from bioem_b200.cases import CASES
     return {"value": round(n / s, 1), "unit": "likelihoods/s", "cores": threads, "kind": "reference",
-            # FFTW is not in this image: the reference's 9 FFTW symbols are served by oracle/fftw_shim (builder code)
-            "fft": "shim (oracle/fftw_shim + oracle/fft_core.hpp; libfftw3f absent from the image)",
+            # FFTW is not in this image: the reference's 9 FFTW symbols are served by oracle/fftw_shim, which hands the
+            # transforms to Intel oneMKL when it can (else to its built-in engine)
+            "fft": FFT_LABEL[_LAST_FFT["engine"]],
             "fft_microbench": _fft_microbench(CASES[WORKLOADS[workload][0]].n_pixels),
             "reference_stage_totals_s": stages or None,
-            "sample": f"unmodified reference (FFTW-API shim FFT, Algo 1, OpenMP {threads} threads) on the first "
+            "sample": f"unmodified reference ({_LAST_FFT['engine']} FFT behind the FFTW-API shim, Algo 1, OpenMP {threads} threads) on the first "
                       f"{n_or} orientations x all CTFs x {n_part} particles of {workload} = {n} likelihoods in {s:.2f} s "
                       f"(reference's own run() timer)"}
 
@@ -462,8 +486,20 @@ def _fft_microbench(n: int) -> dict | None:
         for _ in range(reps):
             np.fft.irfft2(Z, s=(n, n))
         t_np = (time.perf_counter() - t0) / reps
-        return {"n": n, "shim_c2r_us": round(1e6 * t_shim, 1), "numpy_pocketfft_c2r_us": round(1e6 * t_np, 1),
-                "note": "one core, one N x N c2r transform = the FFT work of one likelihood"}
+        out = {"n": n, "builtin_shim_c2r_us": round(1e6 * t_shim, 1), "numpy_pocketfft_c2r_us": round(1e6 * t_np, 1),
+               "note": "one core, one N x N c2r transform = the FFT work of one likelihood"}
+        try:  # torch.fft on CPU is the same oneMKL the reference arm uses
+            import torch
+            torch.set_num_threads(1)
+            zt = torch.from_numpy(Z)
+            torch.fft.irfft2(zt, s=(n, n))
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                torch.fft.irfft2(zt, s=(n, n))
+            out["mkl_c2r_us"] = round(1e6 * (time.perf_counter() - t0) / reps, 1)
+        except Exception:
+            pass
+        return out
     except Exception as e:  # a side number
         return {"error": str(e)[:200]}
 
@@ -525,8 +561,8 @@ def run_reference(args):
                 times.append(s)
     total = sum(times)
     value = n * len(times) / total
-    sample = (f"each step = unmodified reference (oracle/_ref/bioEM_ref: reference sources + FFTW-API shim FFT, "
-              f"Algo 1, OpenMP {threads} threads) on the first {n_or} orientations x {case.n_ctf} CTFs x {n_part} "
+    sample = (f"each step = unmodified reference (oracle/_ref/bioEM_ref: reference sources + FFTW-API shim, FFT engine = "
+              f"{_LAST_FFT['engine']}, Algo 1, OpenMP {threads} threads) on the first {n_or} orientations x {case.n_ctf} CTFs x {n_part} "
               f"particles of {args.workload} = {n} likelihoods; time = the reference's own run() timer")
     line = {
         "impl": "reference", "metric": "likelihoods/s", "value": round(value, 1), "unit": "likelihoods/s",
@@ -537,7 +573,7 @@ def run_reference(args):
                                f"{case.n_pixels}x{case.n_pixels}, DISPLACE_CENTER {case.max_disp} {case.grid_space}",
                    "likelihoods_per_step": n, "parallelism": f"host OpenMP x{threads}"},
         "cpu_baseline": {"value": round(value, 1), "unit": "likelihoods/s", "cores": threads, "kind": "reference",
-                         "fft": "shim (oracle/fftw_shim + oracle/fft_core.hpp; libfftw3f absent from the image)",
+                         "fft": FFT_LABEL[_LAST_FFT["engine"]],
                          "sample": sample},
         "e2e": {"value": round(value, 1), "unit": "likelihoods/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

@@ -26,8 +26,11 @@ CFLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-l
 
 def sizes() -> list[int]:
     src = open(os.path.join(CSRC, "bioem_b200.cu")).read()
-    m = re.search(r"#define BIOEM_SIZES\(X\)(.*)", src)
-    return [int(x) for x in re.findall(r"X\((\d+)\)", m.group(1))]
+    out = []
+    for macro in ("BIOEM_SIZES_TUNED", "BIOEM_SIZES_AUTO"):
+        m = re.search(r"#define " + macro + r"\(X\)(.*)", src)
+        out += [int(x) for x in re.findall(r"X\((\d+)\)", m.group(1))]
+    return out
 
 
 def needs_build() -> bool:

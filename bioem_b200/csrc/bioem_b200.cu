@@ -12,7 +12,10 @@
 
 using namespace bioem;
 
-#define BIOEM_SIZES(X) X(32) X(36) X(48) X(64) X(96) X(100) X(120) X(128) X(144) X(160) X(192) X(200) X(216) X(224) X(240) X(256) X(288) X(300) X(320) X(336) X(360) X(384) X(400) X(420) X(432) X(448) X(480) X(500) X(512)
+// hand-tuned splits (every pruned variant of the fused kernel) and rule-generated ones (unpruned variant only)
+#define BIOEM_SIZES_TUNED(X) X(32) X(36) X(48) X(64) X(96) X(100) X(120) X(128) X(144) X(160) X(192) X(200) X(216) X(224) X(240) X(256) X(288) X(300) X(320) X(336) X(360) X(384) X(400) X(420) X(432) X(448) X(480) X(500) X(512)
+#define BIOEM_SIZES_AUTO(X) X(16) X(18) X(20) X(24) X(28) X(30) X(40) X(42) X(50) X(54) X(56) X(60) X(70) X(72) X(80) X(84) X(90) X(98) X(108) X(112) X(126) X(140) X(150) X(162) X(168) X(180) X(196) X(210) X(250) X(252) X(270) X(280) X(294) X(324) X(350) X(378) X(392) X(450) X(486) X(504)
+#define BIOEM_SIZES(X) BIOEM_SIZES_TUNED(X) BIOEM_SIZES_AUTO(X)
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string &msg)

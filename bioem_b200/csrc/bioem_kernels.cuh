@@ -738,6 +738,8 @@ template <int N> __host__ __device__ constexpr int lik_window_groups(int maxD)
 {
   using L = Lay<N>;
   constexpr int HALF = L::R2 / 2;
+  if (L::G::GENERIC)
+    return HALF; // rule-generated split: only the unpruned variant exists
   const int need = maxD / L::R1 + 1;
   return (need <= 7 && need < HALF) ? need : HALF;
 }
@@ -767,11 +769,13 @@ template <int N> struct LikGeo
   static constexpr int YS0 = L::NCOL + ((KC - L::NCOL) % 16 + 16) % 16;
   static constexpr int YS = YS0 > L::NCOL ? YS0 : YS0 + 16; // index NCOL of a row must exist
   static constexpr int EW = L::R1 * ES;                     // float2 per warp
-  __host__ __device__ static constexpr int nk(int W) { return 2 * W >= L::R2 ? L::R2 : 2 * W; }
+  // W = R2/2 is the "keep everything" variant (lik_window_groups only returns it as the fall-back): all R2 output
+  // groups, also the middle one of an odd R2
+  __host__ __device__ static constexpr int nk(int W) { return W >= L::R2 / 2 ? L::R2 : 2 * W; }
   // Above N = 224 one CTA fills an SM and the warp count is what the shared memory leaves: Y then
   // holds exactly the window rows (slot = window row index, nwp of them) instead of whole radix
   // output groups, which buys two more warps at N = 320 / 360 and the 24 x 16 split at N = 384.
-  static constexpr bool COMPACT = N > 224;
+  static constexpr bool COMPACT = N > 224 || L::G::GENERIC;
   __host__ __device__ static constexpr int rows(int W, int nwp) { return COMPACT ? nwp : nk(W) * L::R1; }
   // BIOEM_TMA (measured variant, profiles/r02_tma_variant.md): one staging slot per warp for the conv and the
   // particle chunk of its next column task, filled by cp.async.bulk

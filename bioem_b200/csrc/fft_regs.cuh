@@ -304,12 +304,18 @@ template <int R, int SIGN, int A> struct Dft
 //   KC  packed spectrum columns per column-pass chunk (NCOL = N/2 must divide)
 //   PC  row pairs per row-pass chunk
 template <int N> struct Geo;
-#define BFFT_GEO(N_, R1_, R2_, KC_, PC_)                                                           \
+//   GENERIC  1: split chosen by rule (tools/gen_geometries.py), only the unpruned variant of the fused kernel
+//            is instantiated, its row slots hold exactly the window rows
+#define BFFT_GEO_(N_, R1_, R2_, KC_, PC_, GEN_)                                                    \
   template <> struct Geo<N_>                                                                       \
   {                                                                                                \
     static constexpr int R1 = R1_, R2 = R2_, KC = KC_, PC = PC_;                                   \
+    static constexpr bool GENERIC = GEN_;                                                          \
     static_assert(R1_ * R2_ == N_ && (R1_ % 2) == 0 && ((N_ / 2) % KC_) == 0, "geometry");         \
+    static_assert(R2_ <= 32 && PC_ * R1_ <= 256 && PC_ * R2_ <= 256, "geometry");                  \
   };
+#define BFFT_GEO(N_, R1_, R2_, KC_, PC_) BFFT_GEO_(N_, R1_, R2_, KC_, PC_, false)
+#define BFFT_GEO_AUTO(N_, R1_, R2_, KC_, PC_) BFFT_GEO_(N_, R1_, R2_, KC_, PC_, true)
 // (R1 even: the packed layout pairs sub-sequences n1 = 2k, 2k+1; R2 <= 32: one lane per sub-sequence in the
 // first radix pass of a warp; PC * max(R1, R2) <= 256)
 BFFT_GEO(32, 4, 8, 16, 16)
@@ -342,6 +348,50 @@ BFFT_GEO(448, 28, 16, 16, 8)
 BFFT_GEO(480, 20, 24, 16, 10)
 BFFT_GEO(500, 20, 25, 10, 10)
 BFFT_GEO(512, 16, 32, 16, 8)
+// every other even edge up to 512 with prime factors 2 / 3 / 5 / 7 (490 = 2 * 5 * 7^2 has no split with an even
+// R1 <= 32 and R2 <= 32), generated by tools/gen_geometries.py
+BFFT_GEO_AUTO(16, 4, 4, 8, 16)
+BFFT_GEO_AUTO(18, 6, 3, 9, 16)
+BFFT_GEO_AUTO(20, 4, 5, 10, 16)
+BFFT_GEO_AUTO(24, 12, 2, 12, 16)
+BFFT_GEO_AUTO(28, 14, 2, 14, 16)
+BFFT_GEO_AUTO(30, 6, 5, 15, 16)
+BFFT_GEO_AUTO(40, 8, 5, 20, 16)
+BFFT_GEO_AUTO(42, 14, 3, 21, 16)
+BFFT_GEO_AUTO(50, 10, 5, 5, 16)
+BFFT_GEO_AUTO(54, 18, 3, 9, 14)
+BFFT_GEO_AUTO(56, 8, 7, 14, 16)
+BFFT_GEO_AUTO(60, 20, 3, 15, 12)
+BFFT_GEO_AUTO(70, 14, 5, 7, 16)
+BFFT_GEO_AUTO(72, 8, 9, 18, 16)
+BFFT_GEO_AUTO(80, 20, 4, 20, 12)
+BFFT_GEO_AUTO(84, 6, 14, 21, 16)
+BFFT_GEO_AUTO(90, 10, 9, 15, 16)
+BFFT_GEO_AUTO(98, 14, 7, 7, 16)
+BFFT_GEO_AUTO(108, 12, 9, 18, 16)
+BFFT_GEO_AUTO(112, 14, 8, 14, 16)
+BFFT_GEO_AUTO(126, 14, 9, 21, 16)
+BFFT_GEO_AUTO(140, 10, 14, 14, 16)
+BFFT_GEO_AUTO(150, 6, 25, 15, 10)
+BFFT_GEO_AUTO(162, 18, 9, 9, 14)
+BFFT_GEO_AUTO(168, 12, 14, 21, 16)
+BFFT_GEO_AUTO(180, 18, 10, 18, 14)
+BFFT_GEO_AUTO(196, 14, 14, 14, 16)
+BFFT_GEO_AUTO(210, 10, 21, 21, 12)
+BFFT_GEO_AUTO(250, 10, 25, 5, 10)
+BFFT_GEO_AUTO(252, 18, 14, 21, 14)
+BFFT_GEO_AUTO(270, 10, 27, 15, 9)
+BFFT_GEO_AUTO(280, 20, 14, 20, 12)
+BFFT_GEO_AUTO(294, 14, 21, 21, 12)
+BFFT_GEO_AUTO(324, 12, 27, 18, 9)
+BFFT_GEO_AUTO(350, 14, 25, 7, 10)
+BFFT_GEO_AUTO(378, 14, 27, 21, 9)
+BFFT_GEO_AUTO(392, 28, 14, 14, 9)
+BFFT_GEO_AUTO(450, 18, 25, 15, 10)
+BFFT_GEO_AUTO(486, 18, 27, 9, 9)
+BFFT_GEO_AUTO(504, 18, 28, 21, 9)
 #undef BFFT_GEO
+#undef BFFT_GEO_AUTO
+#undef BFFT_GEO_
 
 } // namespace bfft

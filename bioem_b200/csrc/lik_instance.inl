@@ -29,6 +29,10 @@ extern "C" cudaError_t BIOEM_CAT(bioem_lik_launch_, BIOEM_N)(const bioem::LikPar
 #ifdef BIOEM_ONLY_W // experiments (tools/build_variant.py): compile a single window-group variant
   return w == BIOEM_ONLY_W ? bioem::lik_launch_w<BIOEM_ONLY_W>(*p, nblocks, s) : cudaErrorInvalidValue;
 #else
+  if constexpr (L::G::GENERIC)
+    return bioem::lik_launch_w<(HALF > 0 ? HALF : 1)>(*p, nblocks, s);
+  else
+  {
   if (w == 1 && HALF > 1)
     return bioem::lik_launch_w<1>(*p, nblocks, s);
   if constexpr (HALF > 2)
@@ -50,5 +54,6 @@ extern "C" cudaError_t BIOEM_CAT(bioem_lik_launch_, BIOEM_N)(const bioem::LikPar
     if (w == 7)
       return bioem::lik_launch_w<7>(*p, nblocks, s);
   return bioem::lik_launch_w<HALF>(*p, nblocks, s);
+  }
 #endif
 }

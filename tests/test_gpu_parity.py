@@ -665,14 +665,20 @@ def test_mrc_ingest_on_device_matches_host_reader(setups):
     assert a.tobytes() == b.tobytes()
 
 
-@pytest.mark.parametrize("n,maxd", [(n, min(10, n // 4)) for n in (32, 36, 48, 64, 96, 100, 120, 128, 144, 160, 192, 200, 216, 224, 240,
-                                                                    256, 288, 300, 320, 336, 360, 384, 400, 420, 432, 448, 480,
-                                                                    500, 512)]
-                         + [(200, 40), (300, 40), (448, 40), (512, 40), (100, 7)])
+def _all_edges():
+    from bioem_b200 import build
+    return sorted(build.sizes())
+
+
+@pytest.mark.parametrize("n,maxd", [(n, min(10, n // 4)) for n in _all_edges()]
+                         + [(200, 40), (300, 40), (448, 40), (512, 40), (100, 7),
+                            # windows that need the middle output group of an odd second radix (N = 120 = 8 x 15, 360 = 24 x 15)
+                            (120, 59), (360, 170), (36, 17), (18, 8), (250, 100)])
 def test_every_instantiated_image_edge_matches_oracle(n, maxd):
-    """One tiny run per image edge the kernels are instantiated for (mixed radices 2/3/5/7,
-    one or two CTAs per SM, 4-12 warps): log P and arg-max against the oracle; the largest edges also with the
-    production window DISPLACE_CENTER 40 (shared-memory fit)."""
+    """One tiny run per image edge the kernels are instantiated for -- every even edge from 16 to 512 whose prime
+    factors are 2 / 3 / 5 / 7 except 490 (hand-tuned splits with pruned variants, rule-generated splits with the
+    unpruned variant): log P and arg-max against the oracle; some edges also with the production window
+    DISPLACE_CENTER 40 (shared-memory fit) and with windows close to the whole image."""
     _need_gpu()
     from bioem_b200.cases import CFG1_CTF, Case
     case = Case(f"edge{n}", n, 1.5, 40, 2, 576, 2, CFG1_CTF, maxd, 1,

@@ -30,7 +30,9 @@ def test_supported_sizes():
     L = api.lib()
     for n in (32, 36, 64, 100, 128, 200, 224, 240, 300, 360, 448, 512):
         assert L.bioem_b200_supported_size(n) == 1
-    for n in (31, 102, 225, 1024):
+    for n in (16, 18, 250, 486, 504):  # rule-generated splits
+        assert L.bioem_b200_supported_size(n) == 1
+    for n in (31, 102, 225, 490, 1024):  # odd, a prime factor above 7, no valid two-pass split, too large
         assert L.bioem_b200_supported_size(n) == 0
 
 

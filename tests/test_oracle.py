@@ -142,6 +142,36 @@ def test_reference_binary_live_matches_golden(tmp_path, golden_dir):
     assert (a["cent_x"] == b["cent_x"]).all() and (a["cent_y"] == b["cent_y"]).all()
 
 
+def _mkl_lib():
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("torch")
+        path = os.path.join(os.path.dirname(spec.origin), "lib", "libtorch_cpu.so")
+        return path if os.path.exists(path) else None
+    except Exception:
+        return None
+
+
+@pytest.mark.skipif(not os.path.exists(REFBIN) or _mkl_lib() is None, reason="reference binary or MKL-carrying libtorch_cpu.so absent")
+@pytest.mark.parametrize("name", ["toy32", "toy36g2", "toy64"])
+def test_reference_with_vendor_fft_matches_golden(name, tmp_path, golden_dir):
+    """FFTW is not in the image, so the golden files were made with the shim's built-in FFT engine (builder code).
+    The same unmodified reference with Intel oneMKL doing the transforms (BIOEM_FFT_MKL_LIB -> oracle/fftw_shim binds
+    DFTI at run time; this is what bench.py's reference arm times) must reproduce them: same arg-max records, log P
+    within the Q7 noise floor."""
+    cd = build_case(name, str(tmp_path))
+    r = subprocess.run([REFBIN] + reference_cli(cd), cwd=str(tmp_path), capture_output=True, text=True,
+                       env={**os.environ, "OMP_NUM_THREADS": "2", "BIOEM_FFT_MKL_LIB": _mkl_lib()})
+    assert r.returncode == 0, r.stdout[-1000:]
+    if "Intel oneMKL" not in r.stdout:
+        pytest.skip("libtorch_cpu.so does not export the DFTI entry points here")
+    a = parse_output_probabilities(os.path.join(tmp_path, "Output_Probabilities"))
+    b = parse_output_probabilities(os.path.join(golden_dir, name, "Output_Probabilities"))
+    np.testing.assert_allclose(a["logp"], b["logp"], atol=LOGP_ATOL[cd.case.n_pixels])
+    assert (a["cent_x"] == b["cent_x"]).all() and (a["cent_y"] == b["cent_y"]).all()
+    np.testing.assert_allclose(a["angles"], b["angles"], atol=1.1e-4)
+
+
 def test_displacement_count_quirk_q3():
     L = pyoracle.lib()
     assert L.oracle_num_displacements(224, 40, 1) == 81 * 81
