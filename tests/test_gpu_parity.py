@@ -566,6 +566,18 @@ def test_exact_ties_between_ctfs_orientations_groups_and_launches(monkeypatch, s
         e.close()
 
 
+def test_window_that_does_not_fit_is_refused_loudly():
+    """The row slots of the fused kernel hold (window rows) x (N/2 + 1) complex values in shared memory: a window the
+    SM cannot hold is refused at create() with a message, never truncated (the reference itself accepts any window)."""
+    _need_gpu()
+    from bioem_b200.cases import CFG1_CTF, Case
+    case = Case("toobig", 360, 1.5, 40, 1, 576, 1, CFG1_CTF, 170, 1, model_sigma=30.0, model_rmax=90.0, particle_format="mrc")
+    cd = build_case(case)
+    hi, parts = api.inputs_for_case(cd)
+    with pytest.raises(api.BioemError, match="does not fit in shared memory"):
+        api.Engine(hi.cfg)
+
+
 def test_particle_upload_paths_agree(setups):
     """upload_particles (device FFT) and upload_particles_fft (host-provided spectra) give the
     same result up to FFT rounding."""
@@ -672,8 +684,8 @@ def _all_edges():
 
 @pytest.mark.parametrize("n,maxd", [(n, min(10, n // 4)) for n in _all_edges()]
                          + [(200, 40), (300, 40), (448, 40), (512, 40), (100, 7),
-                            # windows that need the middle output group of an odd second radix (N = 120 = 8 x 15, 360 = 24 x 15)
-                            (120, 59), (360, 170), (36, 17), (18, 8), (250, 100)])
+                            # windows that need the middle output group of an odd second radix (N = 120 = 8 x 15, 18 = 6 x 3)
+                            (120, 59), (36, 17), (18, 8), (250, 60)])
 def test_every_instantiated_image_edge_matches_oracle(n, maxd):
     """One tiny run per image edge the kernels are instantiated for -- every even edge from 16 to 512 whose prime
     factors are 2 / 3 / 5 / 7 except 490 (hand-tuned splits with pruned variants, rule-generated splits with the

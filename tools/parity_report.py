@@ -12,7 +12,8 @@ from bioem_b200 import api  # noqa: E402
 from bioem_b200.cases import build_case  # noqa: E402
 from oracle import pyoracle  # noqa: E402
 
-names = sys.argv[1:] or ["toy32", "toy32psf", "toy36g2", "toy64", "cfg1", "cfg2_slice", "cfg5_slice", "cfg4_slice"]
+names = sys.argv[1:] or ["toy32", "toy32psf", "toy32g2odd", "toy32g3", "toy36g2", "toy64", "cfg1", "cfg2_slice", "cfg5_slice",
+                         "cfg4_slice", "cfg4_voxel_slice"]
 print("| case | N | images | likelihoods | max abs d logP | max rel d logP | identical arg-max | near-tie gaps (oracle logpro) |")
 print("|---|---|---|---|---|---|---|---|")
 for name in names:

@@ -89,7 +89,7 @@ def post(label, rnd):
     t["likelihood_kernel<224>"] = {
         "dram_bytes_per_likelihood": round((rd * scale[ur] + wr * scale[uw]) / NLIK, 1),
         # what actually binds (the roofline "frac" of bench.py is the algorithmic ratio of SURVEY 8d, not DRAM utilisation)
-        "dram_pct_of_peak": pct("dram__throughput.avg.pct_of_peak_sustained_elapsed"),
+        "dram_pct_of_peak": pct("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
         "lsu_data_pipe_pct": pct("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"),
         "fma_pipe_pct": pct("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
         "issue_slot_pct": pct("smsp__issue_active.avg.pct_of_peak_sustained_active"),
