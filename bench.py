@@ -367,7 +367,9 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(d2h), "steps": e2e_steps},
             "gpu_launches": int(total_launches),
             "roofline": roof,
-            "exact_argmax_pass": {"records": refine[0], "displacement_corrected": refine[1], "disagreed": refine[2]},
+            # the pass that evaluates the arg-max displacement of every particle's winning likelihood with the reference's
+            # first-of-ties rule (exact_argmax_kernel): records evaluated / re-evaluations that did not reproduce the logpro
+            "exact_argmax_pass": {"records": refine[0], "disagreed": refine[2]},
             "wall_s_timed_region": round(t_wall, 3),
         }
         if result_check is not None:

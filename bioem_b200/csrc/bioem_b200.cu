@@ -1011,10 +1011,10 @@ static int refine_argmax(bioem_b200_context *h)
 {
   if (h->argmax_exact)
     return BIOEM_B200_OK;
-  if (getenv("BIOEM_B200_NO_EXACT_ARGMAX"))
-    return BIOEM_B200_OK;
+  // (the fused kernel does not track displacements at all, so this pass is what fills them in)
   if (h->A <= 0 || h->O <= 0 || h->C <= 0 || h->M <= 0 || (int) h->h_angles.size() != h->O)
-    return BIOEM_B200_OK; // inputs were replaced since the run: nothing to re-evaluate against
+    return fail(BIOEM_B200_ERR_STATE, "download: the arg-max displacement is evaluated on this handle and needs its model, "
+                                      "orientations, CTF table and particles (upload them before importing partials)");
   RC(ensure_batch(h));
   const int M = h->M;
   std::vector<Running> st((size_t) M);

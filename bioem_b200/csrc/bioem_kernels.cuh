@@ -793,7 +793,7 @@ template <int N> struct LikGeo
 template <int N> __host__ __device__ constexpr int lik_window_groups(int maxD);
 
 // likelihoods whose double-precision bookkeeping is deferred, then done by that many lanes of warp 0
-// at once (16: the ring of a CTA fits next to the row slots and exchange tiles at every size)
+// at once
 template <int N> __host__ __device__ constexpr int lik_pending() { return 16; }
 
 // warps per CTA of the fused kernel.  From N = 160 to 224 two CTAs of 8 warps share an SM.  Measured
@@ -909,13 +909,13 @@ struct BookState
 //   * row pass, same structure: two real rows per complex transform, through the same tile,
 //   * the displacement-dependent factor of the analytic log-posterior (firstele, FP32,
 //     reference operation order, two displacements per packed instruction) straight out of
-//     the FFT registers; every thread keeps an ONLINE (min firstele <=> max logpro, its
-//     enumeration index and correlation value, sum of exp relative to that minimum, re-based
-//     when the minimum moves); REDUX minima and a shuffle sum combine the lanes into one ring
-//     entry per warp,
-//   * the bookkeeping (double-precision log, float narrowing, first-of-ties rule over the
-//     near-minimum candidates, log-sum-exp fold into the image's running state) is deferred:
-//     warp 0 does it for lik_pending<N>() = 16 likelihoods at once, one per lane.
+//     the FFT registers; every thread keeps an ONLINE (min firstele <=> max logpro, sum of exp
+//     relative to that minimum, re-based when the minimum moves); a REDUX minimum and a shuffle
+//     sum combine the lanes into one ring entry per warp,
+//   * the bookkeeping (double-precision log, float narrowing, log-sum-exp fold into the image's
+//     running state, arg-max (orientation, CTF)) is deferred: warp 0 does it for lik_pending<N>()
+//     = 16 likelihoods at once, one per lane.  The displacement of the arg-max is NOT tracked here:
+//     exact_argmax_kernel re-evaluates every particle's winning likelihood at download.
 // All butterflies run on packed FP32x2 instructions.  Per likelihood one CTA barrier (columns
 // -> rows) and one split-phase mbarrier (rows -> next columns: arrive, run the first radix pass
 // of the next likelihood's first chunk, wait); no correlation map ever leaves the SM.
@@ -944,13 +944,10 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
   float4 *OPS = reinterpret_cast<float4 *>(RS + 256) + (size_t) (threadIdx.x >> 5) * 2 * CHUNK4; // [conv chunk][particle chunk]
   __shared__ unsigned long long s_tbar[NWARP];
 #endif
-  // ring of likelihoods waiting for their bookkeeping, one entry per warp and likelihood:
-  // minimum key (firstele bits << 32 | enumeration index), runner-up candidate (enumeration index
-  // << 32 | firstele bits), sum of exp relative to the warp minimum, correlation value at the minimum
-  __shared__ unsigned long long s_wk[NPEND][NWARP];
-  __shared__ unsigned long long s_wc[NPEND][NWARP];
+  // ring of likelihoods waiting for their bookkeeping, one entry per warp and likelihood: the warp's minimum of
+  // firstele (bit pattern: positive floats order like their bits) and its sum of exp relative to that minimum
+  __shared__ unsigned s_wk[NPEND][NWARP];
   __shared__ float s_ws[NPEND][NWARP];
-  __shared__ float s_wv[NPEND][NWARP];
   __shared__ int s_poc[NPEND];
   __shared__ unsigned long long s_mbar; // closing barrier of a likelihood (one arrival per warp)
   __shared__ BookState s_bk;
@@ -1060,78 +1057,28 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
   auto flush = [&](int npend) {
     __syncwarp();
     const bool act = lane < npend;
-    float lpf = __int_as_float(0xff800000), S = 0.f, bvv = 0.f, fminl = 1.f;
-    int lin = 0, oc = 0;
+    float lpf = __int_as_float(0xff800000), S = 0.f;
+    int oc = 0;
     ConvParam cpl;
     cpl.sumC = cpl.sumsqC = 0.f;
     if (act)
     {
-      unsigned long long kmin = ~0ull;
-      int wb = 0;
+      unsigned fbmin = 0xffffffffu;
 #pragma unroll
       for (int w = 0; w < NWARP; w++)
-      {
-        const unsigned long long k = s_wk[lane][w];
-        if (k < kmin)
-        {
-          kmin = k;
-          wb = w;
-        }
-      }
+        fbmin = min(fbmin, s_wk[lane][w]);
       oc = s_poc[lane];
       cpl = p.cpar[oc];
-      const float fmin = __uint_as_float((unsigned) (kmin >> 32));
+      const float fmin = __uint_as_float(fbmin);
       const float inv = __fdiv_rn(1.f, fmin);
-      fminl = fmin;
       lpf = (float) __fma_rn(p.acoef_d, log((double) fmin), cpl.Bterm);
-      lin = (int) (kmin & 0xffffffffu);
-      bvv = s_wv[lane][wb];
 #pragma unroll 1
       for (int w = 0; w < NWARP; w++)
-      {
-        const float fw = __uint_as_float((unsigned) (s_wk[lane][w] >> 32));
-        S += s_ws[lane][w] * expa1p((fw - fmin) * inv);
-      }
+        S += s_ws[lane][w] * expa1p((__uint_as_float(s_wk[lane][w]) - fmin) * inv);
     }
-    // Every firstele within 64 ulps of the minimum may share its float-narrowed logpro; the
-    // reference keeps the FIRST of them in enumeration order (bioem_algorithm.h:84-96).  The warps'
-    // minima and runner-ups with a lower enumeration index are examined exactly, lowest index
-    // first (warp-uniform loop: a round costs one double-precision log, and rounds are rare).
-    int tried = -1; // candidates up to this enumeration index have been examined
-#pragma unroll 1
-    for (int round = 0; round < 4; round++)
-    {
-      int lc = 0x7fffffff;
-      float fc = 0.f;
-      if (act)
-      {
-        const float fthr = __uint_as_float(__float_as_uint(fminl) + 64u);
-#pragma unroll 1
-        for (int w = 0; w < 2 * NWARP; w++)
-        {
-          const unsigned long long k = (w < NWARP) ? s_wk[lane][w] : s_wc[lane][w - NWARP];
-          // minima carry (firstele bits << 32 | index), runner-ups (index << 32 | firstele bits)
-          const int l = (w < NWARP) ? (int) (k & 0xffffffffu) : (int) (k >> 32);
-          const float f = __uint_as_float((w < NWARP) ? (unsigned) (k >> 32) : (unsigned) (k & 0xffffffffu));
-          if (k != ~0ull && f <= fthr && l < lin && l > tried && l < lc)
-          {
-            lc = l;
-            fc = f;
-          }
-        }
-      }
-      if (__ballot_sync(0xffffffffu, lc != 0x7fffffff) == 0u)
-        break;
-      if (lc != 0x7fffffff)
-      {
-        tried = lc;
-        if ((float) __fma_rn(p.acoef_d, log((double) fc), cpl.Bterm) == lpf)
-        {
-          lin = lc;
-          tried = 0x7ffffffe; // done: nothing with a lower index is left
-        }
-      }
-    }
+    // (WHICH displacement attains the maximum is not tracked: logpro is narrowed to float before it is compared, so
+    // displacements tie and the first in enumeration order keeps the record, bioem_algorithm.h:84-96 -- the exact pass
+    // at download, exact_argmax_kernel, applies that rule to the whole window of every particle's winning likelihood)
     // arg-max of the batch: greatest lpf, lowest lane (= first in enumeration order) on ties
     unsigned long long key = ((unsigned long long) float_ordered(lpf) << 32) | (unsigned) (31 - lane);
 #pragma unroll
@@ -1155,8 +1102,8 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
         s_bk.lpf = lpfmax;
         s_bk.o = p.o_base + oc / p.C;
         s_bk.c = oc % p.C;
-        s_bk.lin = lin;
-        s_bk.v = bvv;
+        s_bk.lin = 0; // displacement index and correlation value: filled in by the exact pass
+        s_bk.v = 0.f;
         s_bk.sC = cpl.sumC;
         s_bk.ssC = cpl.sumsqC;
       }
@@ -1387,8 +1334,7 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
       // ------------------------------------------------ row pass (along ky), 2 rows per transform
       // running minimum of firstele of this thread, its enumeration index and correlation value,
       // and the sum of exp(logpro - logpro at that minimum) over everything seen so far
-      float bfe = FE_NONE, binv = 1.f / FE_NONE, bv = 0.f;
-      int blin = 0x7fffffff;
+      float bfe = FE_NONE, binv = 1.f / FE_NONE;
       float2 S2 = make_float2(0.f, 0.f);
       const int npairs = nwp / 2;
       for (int p0 = warp * KC; p0 < npairs; p0 += NWARP * KC)
@@ -1479,35 +1425,13 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
 #pragma unroll
             for (int j = 1; j < NK; j++)
               mn = fminf(mn, fminf(fe[j].x, fe[j].y));
-            if (mn <= bfe)
+            // The displacement index of the maximum is not tracked here at all: the exact pass at download
+            // (exact_argmax_kernel) re-evaluates the winning likelihood of every particle and applies the reference's
+            // first-of-ties rule to its whole window.  Only the running minimum and the sum of exp relative to it remain.
+            if (mn < bfe)
             {
-              // (taken by a warp for most items: some lane has a new minimum)  Position of the item's
-              // minimum: the window index of a row grows with j (wtab: displacements 0..maxD, then
-              // -maxD..-1, both ascending in the raw row number), so scanning row wa + 1 before row wa and j
-              // downwards visits the enumeration indices in descending order -- the last match is the
-              // first in the reference's enumeration order.
-              int code = 0;
-              float vs = 0.f;
-              bfft::static_for<0, 2 * NK>([&](auto i_) {
-                constexpr int i = decltype(i_)::value;
-                constexpr int j = NK - 1 - (i % NK);
-                constexpr bool second = i < NK;
-                if ((second ? fe[j].y : fe[j].x) == mn)
-                {
-                  code = 2 * j + (second ? 1 : 0);
-                  vs = second ? y[k2_of(j)].y : y[k2_of(j)].x;
-                }
-              });
-              const int jj = code >> 1;
-              const int lin = (wa + (code & 1)) * nw + WT[k1 + R1 * ((NK == R2 || jj < W) ? jj : R2 - NK + jj)];
               const float old = bfe;
-              if (mn < bfe || (mn == bfe && lin < blin)) // ties are resolved by the enumeration index
-              {
-                bfe = mn;
-                blin = lin;
-                bv = vs * p.invNN;
-              }
-              // what has been summed so far is re-based onto the new minimum
+              bfe = mn;
               binv = rcp_approx(bfe); // scales the arguments of the exp-sum only (error 1e-7 relative)
               const float sc = expa1p((old - bfe) * binv);
               S2 = __fmul2_rn(S2, make_float2(sc, sc));
@@ -1541,26 +1465,15 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
       // (warp-wide integer minima are single REDUX instructions; firstele is positive, so its bit
       // pattern orders like the value)
       const unsigned fb = __float_as_uint(bfe);
-      const unsigned long long best = ((unsigned long long) fb << 32) | (unsigned) blin;
       const unsigned wfb = __reduce_min_sync(0xffffffffu, fb);
-      const unsigned wlin = __reduce_min_sync(0xffffffffu, fb == wfb ? (unsigned) blin : 0xffffffffu);
-      const unsigned long long wbest = ((unsigned long long) wfb << 32) | wlin;
       const float fw = __uint_as_float(wfb);
       float S = (S2.x + S2.y) * expa1p((bfe - fw) * rcp_approx(fw));
-      // runner-up: the lowest enumeration index among the other threads' minima within 64 ulps
-      const bool iscand = best != wbest && bfe <= __uint_as_float(wfb + 64u);
-      const unsigned cl = __reduce_min_sync(0xffffffffu, iscand ? (unsigned) blin : 0xffffffffu);
-      const unsigned cf = __reduce_min_sync(0xffffffffu, (iscand && (unsigned) blin == cl) ? fb : 0xffffffffu);
-      const unsigned long long cand = cl == 0xffffffffu ? ~0ull : (((unsigned long long) cl << 32) | cf);
 #pragma unroll
       for (int s = 16; s > 0; s >>= 1)
         S += __shfl_xor_sync(0xffffffffu, S, s);
-      if (best == wbest)
-        s_wv[slot][warp] = bv;
       if (lane == 0)
       {
-        s_wk[slot][warp] = wbest;
-        s_wc[slot][warp] = cand;
+        s_wk[slot][warp] = wfb;
         s_ws[slot][warp] = S;
       }
       // Closing barrier, split: arrive (this warp is done with Y, its ring entry is written), then
