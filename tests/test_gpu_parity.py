@@ -571,7 +571,7 @@ def test_window_that_does_not_fit_is_refused_loudly():
     SM cannot hold is refused at create() with a message, never truncated (the reference itself accepts any window)."""
     _need_gpu()
     from bioem_b200.cases import CFG1_CTF, Case
-    case = Case("toobig", 360, 1.5, 40, 1, 576, 1, CFG1_CTF, 170, 1, model_sigma=30.0, model_rmax=90.0, particle_format="mrc")
+    case = Case("toobig", 360, 1.5, 40, 1, 576, 1, CFG1_CTF, 100, 1, model_sigma=30.0, model_rmax=90.0, particle_format="mrc")
     cd = build_case(case)
     hi, parts = api.inputs_for_case(cd)
     with pytest.raises(api.BioemError, match="does not fit in shared memory"):
