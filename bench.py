@@ -555,7 +555,10 @@ def run_reference(args):
         n_part = min(m_full, max(64, 4 * threads))
         n, s = _ref_slice(args.workload, 2, n_part, os.path.join(d, "probe"), threads)
         per_orient = s / 2
-        n_or = int(max(2, min(o_full, args.cpu_seconds / max(per_orient, 1e-9))))
+        # every step is one run of the reference on a slice; the slice is sized so that warm-up + steps stay within
+        # about three minutes of CPU work in total
+        per_step = min(args.cpu_seconds, 180.0 / max(1, args.steps + args.warmup))
+        n_or = int(max(2, min(o_full, per_step / max(per_orient, 1e-9))))
         times = []
         for k in range(args.warmup + args.steps):
             n, s = _ref_slice(args.workload, n_or, n_part, os.path.join(d, f"s{k}"), threads)

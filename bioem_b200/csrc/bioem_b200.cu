@@ -294,7 +294,7 @@ static cudaError_t launch_conv(const float4 *proj, const float4 *ctf, const doub
 // dynamic + (an upper bound of the) static shared memory of the fused kernel
 template <int N> static size_t lik_smem(int maxD, int nwp)
 {
-  return lik_smem_bytes<N>(maxD, nwp) + (size_t) lik_pending<N>() * LikSmem<N>::NWARP * 24 + 256;
+  return lik_smem_bytes<N>(maxD, nwp) + (size_t) lik_pending<N>() * LikSmem<N>::NWARP * 8 + 512;
 }
 
 static cudaError_t do_pack(int N, const float2 *src, float4 *dst, int nmaps, cudaStream_t s)

@@ -793,8 +793,12 @@ template <int N> struct LikGeo
 template <int N> __host__ __device__ constexpr int lik_window_groups(int maxD);
 
 // likelihoods whose double-precision bookkeeping is deferred, then done by that many lanes of warp 0
-// at once
-template <int N> __host__ __device__ constexpr int lik_pending() { return 16; }
+// at once (32: one per lane -- the double-precision log / exp sequence costs warp 0 the same ~1,700 instructions
+// whether 16 or 32 lanes are busy, and the other warps end up waiting for it at the next barrier)
+#ifndef BIOEM_NPEND
+#define BIOEM_NPEND 32
+#endif
+template <int N> __host__ __device__ constexpr int lik_pending() { return BIOEM_NPEND; }
 
 // warps per CTA of the fused kernel.  From N = 160 to 224 two CTAs of 8 warps share an SM.  Measured
 // on B200 at N = 224 (tools/build_variant.py): 8 warps 55.1 ns/likelihood, 7 warps (which would
@@ -817,7 +821,7 @@ template <int N> __host__ __device__ constexpr int lik_warps()
     return 8;
   constexpr size_t budget = 227 * 1024 - 1024;
   for (int nw = 12; nw > 8; nw -= 2)
-    if (LikGeo<N>::dyn_bytes(lik_window_groups<N>(40), nw, 82) + (size_t) lik_pending<N>() * nw * 24 + 256 <= budget)
+    if (LikGeo<N>::dyn_bytes(lik_window_groups<N>(40), nw, 82) + (size_t) lik_pending<N>() * nw * 8 + 512 <= budget)
       return nw;
   return 8;
 #endif
@@ -931,6 +935,12 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
   constexpr bool COMPACT = SM::G::COMPACT;
   constexpr int P2 = (KC * R1 + 31) / 32; // pass-2 trips
   constexpr int NPEND = lik_pending<N>();
+  // window mask folded into the last term of firstele instead of FSEL (P2 * NK more registers).  Measured at N = 224:
+  // 47.2 ns with, 46.7 ns without (fewer instructions, but the extra live registers cost more) -- off.
+#ifndef BIOEM_AMASK
+#define BIOEM_AMASK 0
+#endif
+  constexpr bool AMASK = BIOEM_AMASK && P2 * NK <= 8;
   auto k2_of = [](int j) { return (NK == R2) ? j : (j < W ? j : R2 - NK + j); };
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1320,6 +1330,13 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
       const float f_b = __fmul_rn(__fmul_rn(2.f, sR), cp.sumC);
       const float f_c = __fmul_rn(__fmul_rn(ssR, cp.sumC), cp.sumC);
       const float f_d = __fmul_rn(__fmul_rn(sR, sR), cp.sumsqC);
+      float mfd[AMASK ? P2 * NK : 1];
+      if constexpr (AMASK)
+      {
+#pragma unroll
+        for (int q = 0; q < P2 * NK; q++)
+          mfd[q] = ((vmask >> q) & 1u) ? -f_d : FE_INVALID;
+      }
 
       // ------------------------------------------------ column pass (along kx), per warp
       for (int ch = ch0; ch < NCH; ch += NWARP)
@@ -1416,10 +1433,21 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
               // -O3 -ffast-math -march=native, is free to contract here too, quirk Q7.)
               f = __ffma2_rn(make_float2(Nt, Nt), f, __fmul2_rn(make_float2(f_b, f_b), v));
               f = __fadd2_rn(f, make_float2(-f_c, -f_c));
-              f = __fadd2_rn(f, make_float2(-f_d, -f_d));
-              const bool val = (vmask >> (t * NK + j)) & 1u;
-              fe[j].x = val ? f.x : FE_INVALID;
-              fe[j].y = (val && vb) ? f.y : FE_INVALID;
+              if constexpr (AMASK)
+              {
+                // the last term doubles as the window mask: -f_d for a window column, FE_INVALID (which swallows the
+                // value) for the few outputs of the kept radix groups that lie outside the window.  The padding row of
+                // an odd window is a copy of the last row: it cannot move the minimum and is kept out of the sum below.
+                f = __fadd2_rn(f, make_float2(mfd[t * NK + j], mfd[t * NK + j]));
+                fe[j] = f;
+              }
+              else
+              {
+                f = __fadd2_rn(f, make_float2(-f_d, -f_d));
+                const bool val = (vmask >> (t * NK + j)) & 1u;
+                fe[j].x = val ? f.x : FE_INVALID;
+                fe[j].y = (val && vb) ? f.y : FE_INVALID;
+              }
             });
             float mn = fminf(fe[0].x, fe[0].y);
 #pragma unroll
@@ -1442,7 +1470,10 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
               float2 ll = __ffma2_rn(tt, make_float2(c3, c3), make_float2(c2, c2));
               ll = __ffma2_rn(tt, ll, make_float2(c1, c1));
               ll = __fmul2_rn(tt, ll);
-              S2 = __fadd2_rn(S2, make_float2(ex2_ftz(ll.x), ex2_ftz(ll.y)));
+              if constexpr (AMASK)
+                S2 = __ffma2_rn(make_float2(ex2_ftz(ll.x), ex2_ftz(ll.y)), make_float2(1.f, vb ? 1.f : 0.f), S2);
+              else
+                S2 = __fadd2_rn(S2, make_float2(ex2_ftz(ll.x), ex2_ftz(ll.y)));
             });
             if (p.dbg_values)
               bfft::static_for<0, NK>([&](auto j_) {
