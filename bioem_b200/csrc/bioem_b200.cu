@@ -1172,6 +1172,45 @@ int bioem_b200_import_partials(bioem_b200_handle h, const void *device_gathered,
 }
 
 // ---------------------------------------------------------------- multi-GPU merge inside the library
+// Let kernels on device `reader` (the current device) dereference this library's buffers on device `owner`.  The
+// buffers come from the owner's stream-ordered memory pool (cudaMallocAsync), whose allocations are NOT covered by
+// cudaDeviceEnablePeerAccess: the pool itself has to grant the reader access (cudaMemPoolSetAccess).
+static bool enable_peer_read(int reader, int owner)
+{
+  if (reader == owner)
+    return true;
+  int can = 0;
+  if (cudaDeviceCanAccessPeer(&can, reader, owner) != cudaSuccess || !can)
+  {
+    cudaGetLastError();
+    return false;
+  }
+  const cudaError_t e = cudaDeviceEnablePeerAccess(owner, 0);
+  if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+  {
+    cudaGetLastError();
+    return false;
+  }
+  cudaGetLastError();
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, owner) != cudaSuccess)
+  {
+    cudaGetLastError();
+    return false;
+  }
+  cudaMemAccessDesc desc;
+  memset(&desc, 0, sizeof(desc));
+  desc.location.type = cudaMemLocationTypeDevice;
+  desc.location.id = reader;
+  desc.flags = cudaMemAccessFlagsProtReadWrite;
+  if (cudaMemPoolSetAccess(pool, &desc, 1) != cudaSuccess)
+  {
+    cudaGetLastError();
+    return false;
+  }
+  return true;
+}
+
 int bioem_b200_merge_peers(bioem_b200_handle *hs, int n)
 {
   if (!hs || n <= 0 || n > 16)
@@ -1196,15 +1235,7 @@ int bioem_b200_merge_peers(bioem_b200_handle *hs, int n)
     parts.p[r] = hs[r]->d_state;
     if (hs[r]->device == d->device)
       continue;
-    int can = 0;
-    cudaDeviceCanAccessPeer(&can, d->device, hs[r]->device);
-    if (can)
-    {
-      const cudaError_t e = cudaDeviceEnablePeerAccess(hs[r]->device, 0);
-      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
-        can = 0;
-      cudaGetLastError();
-    }
+    const bool can = enable_peer_read(d->device, hs[r]->device);
     if (!can)
     {
       // no peer mapping (PCIe box without P2P): stage the block with a peer copy instead
@@ -1281,15 +1312,7 @@ int bioem_b200_merge_top_angles_peers(bioem_b200_handle *hs, const int *oBegin, 
   {
     if (hs[r]->device == d->device)
       continue;
-    int can = 0;
-    cudaDeviceCanAccessPeer(&can, d->device, hs[r]->device);
-    if (can)
-    {
-      const cudaError_t e = cudaDeviceEnablePeerAccess(hs[r]->device, 0);
-      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
-        can = 0;
-      cudaGetLastError();
-    }
+    const bool can = enable_peer_read(d->device, hs[r]->device);
     if (!can)
     {
       DevTmp *t = new DevTmp(d);
