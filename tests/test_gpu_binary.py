@@ -18,12 +18,12 @@ EXE = os.path.join(ROOT, "bioem_b200", "bin", "bioEM_b200")
 LOGP_ATOL = {32: 5e-3, 64: 2e-2, 128: 5e-2, 224: 0.3, 360: 1.0}
 
 
-def _run(name, tmp_path, env=None):
+def _run(name, tmp_path, env=None, **overrides):
     if api.lib().bioem_b200_device_count() == 0:
         pytest.fail("no CUDA device visible: the gpu-marked tests must run on the B200 box")
     if not os.path.exists(EXE):
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "bioem_b200", "csrc", "host")])
-    cd = build_case(name, str(tmp_path))
+    cd = build_case(name, str(tmp_path), **overrides)
     r = subprocess.run([EXE] + reference_cli(cd), cwd=tmp_path, capture_output=True, text=True,
                        env={**os.environ, **(env or {})})
     assert r.returncode == 0, r.stdout[-800:] + r.stderr[-800:]
@@ -145,14 +145,16 @@ def test_binary_warns_about_model_points_out_of_frame(tmp_path):
 REF_CUDA = os.path.join(ROOT, "oracle", "_ref", "bioEM_ref_cuda")
 
 
-@pytest.mark.parametrize("name", ["toy64", "cfg2_slice"])
-def test_binary_agrees_with_reference_cuda_path_on_this_gpu(name, tmp_path):
+@pytest.mark.parametrize("name,overrides", [("toy64", {}), ("cfg2_slice", {}),
+                                            # the headline shape: all 1000 particles of cfg2 (224 x 224, 32 CTFs, window 81 x 81)
+                                            ("cfg2", dict(n_particles=1000, n_orient=4))])
+def test_binary_agrees_with_reference_cuda_path_on_this_gpu(name, overrides, tmp_path):
     """The reference's own CUDA path (bioem_cuda.cu + cuFFT, rebuilt for sm_100a by oracle/Makefile) run on
     the same box and the same files: same maximizing orientation / CTF / displacement, log P within 1e-4
     relative.  The checker is executed, never linked: skipped when it was not built."""
     if not os.path.exists(REF_CUDA):
         pytest.skip("oracle/_ref/bioEM_ref_cuda not built")
-    cd = _run(name, tmp_path)
+    cd = _run(name, tmp_path, **overrides)
     os.rename(tmp_path / "Output_Probabilities", tmp_path / "ours")
     r = subprocess.run([REF_CUDA] + reference_cli(cd), cwd=tmp_path, capture_output=True, text=True, timeout=600,
                        env={**os.environ, "GPU": "1", "GPUWORKLOAD": "100", "GPUDEVICE": "0"})

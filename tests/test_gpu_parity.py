@@ -609,6 +609,26 @@ def test_recovers_planted_parameters(setups):
     assert hit >= P.M - 2, (pm["orient"], cd.truth[:, 0])
 
 
+def test_headline_slice_of_64_particles_matches_oracle():
+    """cfg2 at a size the oracle still finishes in seconds: 64 particles x 6 orientations x all 32 CTFs of the
+    production grid at 224 x 224 with the 81 x 81 window (12,288 likelihoods, 80 M log-posterior evaluations)."""
+    _need_gpu()
+    cd = build_case("cfg2", n_particles=64, n_orient=6)
+    hi, parts = api.inputs_for_case(cd)
+    eng = api.Engine(hi.cfg)
+    try:
+        eng.upload_all(hi, parts)
+        eng.run()
+        pm, _ = eng.download()
+        assert eng.exact_argmax_info()[2] == 0
+    finally:
+        eng.close()
+    P = pyoracle.Prepared(cd.case, cd.model, cd.quats, cd.particles)
+    res = P.run()
+    near = _compare_with_oracle(P, hi, pm, res, 224)
+    assert len(near) <= 6, near
+
+
 def test_headline_shape_properties():
     """BASELINE configs[1] shape (1000 particles of 224 x 224, production CTF grid and window) on 340
     orientations -- more than two launches of the fused kernel, an odd tail of the two-orientation groups --
