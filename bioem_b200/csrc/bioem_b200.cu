@@ -1440,6 +1440,8 @@ int bioem_b200_top_angles_nccl(bioem_b200_handle h, int oBegin, int oEnd, int K,
   CU(cudaSetDevice(h->device));
   const size_t rows = (size_t) h->M * K;
   const int R = h->nccl_ranks;
+  if (R > 16)
+    return fail(BIOEM_B200_ERR_INVALID, "top_angles_nccl: more than 16 ranks");
   DevTmp key(h), mine(h), all(h), top(h);
   RC(key.alloc(rows * sizeof(double)));
   RC(mine.alloc(rows * sizeof(TopAngleOut)));
@@ -1451,8 +1453,6 @@ int bioem_b200_top_angles_nccl(bioem_b200_handle h, int oBegin, int oEnd, int K,
   NC(nccl_api()->AllGather(mine.p, all.p, rows * sizeof(TopAngleOut), ncclInt8, (ncclComm_t) h->nccl_comm, h->stream));
   PeerLists lists;
   lists.n = R;
-  if (R > 16)
-    return fail(BIOEM_B200_ERR_INVALID, "top_angles_nccl: more than 16 ranks");
   for (int r = 0; r < R; r++)
     lists.p[r] = all.as<TopAngleOut>() + (size_t) r * rows;
   merge_top_lists_kernel<<<(h->M + 63) / 64, 64, 0, h->stream>>>(lists, h->M, K, key.as<double>(), top.as<TopAngleOut>());
