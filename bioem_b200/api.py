@@ -55,7 +55,7 @@ EXPORTS = [
     "bioem_b200_merge_host", "bioem_b200_merge_peers", "bioem_b200_merge_top_angles_peers",
     "bioem_b200_nccl_unique_id", "bioem_b200_nccl_init", "bioem_b200_nccl_attach", "bioem_b200_nccl_comm", "bioem_b200_merge_nccl",
     "bioem_b200_top_angles_nccl", "bioem_b200_set_kernel_timing", "bioem_b200_out_of_frame",
-    "bioem_b200_exact_argmax_info", "bioem_b200_stream", "bioem_b200_device_angles", "bioem_b200_stats",
+    "bioem_b200_exact_argmax_info", "bioem_b200_cached_product", "bioem_b200_stream", "bioem_b200_device_angles", "bioem_b200_stats",
     "bioem_b200_kernel_time", "bioem_b200_debug_projection", "bioem_b200_debug_convolved",
     "bioem_b200_debug_correlation", "bioem_b200_debug_particle",
     "bioem_b200_host_defocus_to_phase", "bioem_b200_host_ctf_table", "bioem_b200_host_psf_kernels",
@@ -118,6 +118,7 @@ def lib():
     L.bioem_b200_set_kernel_timing.argtypes = [vp, C.c_int]
     L.bioem_b200_out_of_frame.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_longlong)]
     L.bioem_b200_exact_argmax_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.bioem_b200_cached_product.argtypes = [vp]
     L.bioem_b200_stream.argtypes = [vp]
     L.bioem_b200_stream.restype = vp
     L.bioem_b200_device_angles.argtypes = [vp]
@@ -393,6 +394,10 @@ class Engine:
         _chk(lib().bioem_b200_out_of_frame(self._h, per.ctypes.data_as(C.POINTER(C.c_int)), C.byref(tot)),
              "out_of_frame")
         return per, tot.value
+
+    def cached_product(self) -> int:
+        """1: the fused kernel runs in cached-product mode (real CTF kernels), 0: complex conv spectra, -1: undecided."""
+        return int(lib().bioem_b200_cached_product(self._h))
 
     def exact_argmax_info(self):
         """(re-evaluated, corrected, disagreed) of the exact arg-max pass of the last download()."""

@@ -102,6 +102,14 @@ struct bioem_b200_context
   float4 *d_ctf = nullptr;
   double *d_prior = nullptr;
   int C = 0;
+  // cached-product mode of the fused kernel (LikParams::zmode): possible when every CTF kernel is real (CTFs given
+  // in Fourier space), chosen in ensure_batch
+  bool ctf_is_real = false, zmode = false;
+  float4 *d_kreal = nullptr; // [C][kr4] real tables in column-pass order
+  float4 *d_zbuf = nullptr;  // [nslots][map4] scratch maps of the resident CTAs
+  int *d_zflags = nullptr;
+  int nslots = 0;
+  size_t kr4 = 0;
   float4 *d_refs = nullptr;
   float *d_sumRef = nullptr, *d_sumsqRef = nullptr;
   int M = 0;
@@ -209,6 +217,12 @@ static void free_batch(bioem_b200_context *h)
   dfree(h, h->d_conv);
   dfree(h, h->d_cpar);
   dfree(h, h->d_partials);
+  dfree(h, h->d_zbuf);
+  dfree(h, h->d_zflags);
+  h->d_zbuf = nullptr;
+  h->d_zflags = nullptr;
+  h->nslots = 0;
+  h->zmode = false;
   h->d_proj = nullptr;
   h->d_tempden = nullptr;
   h->d_scratch = nullptr;
@@ -233,6 +247,47 @@ static size_t map4_for(int N)
 #undef X
   }
   return 0;
+}
+
+// float4 per CTF of the real table, and how many CTAs of the fused kernel one SM can hold (registers, threads and
+// shared memory; smem = dynamic + static bytes of one CTA) -- the scratch maps of the cached-product mode are sized by it
+template <int N> static void zgeo_of(size_t smem, size_t *kr4, int *ctas)
+{
+  *kr4 = KLay<N>::KR4;
+  const int by_regs = 65536 / (LikSmem<N>::MAXREG * LikSmem<N>::LNT);
+  const int by_thr = 2048 / LikSmem<N>::LNT;
+  const int by_smem = (int) ((size_t) 228 * 1024 / (smem + 1024));
+  *ctas = std::max(1, std::min(std::min(by_regs, by_thr), std::min(by_smem, 32)));
+}
+static void zgeo_for(int N, size_t smem, size_t *kr4, int *ctas)
+{
+  switch (N)
+  {
+#define X(n)                                                                                              \
+  case n:                                                                                                 \
+    zgeo_of<n>(smem, kr4, ctas);                                                                          \
+    return;
+    BIOEM_SIZES(X)
+#undef X
+  }
+}
+template <int N> static cudaError_t launch_kreal(const float4 *ctf, float4 *kreal, int C, cudaStream_t s)
+{
+  dim3 g((KLay<N>::KR4 + 255) / 256, C);
+  kreal_kernel<N><<<g, 256, 0, s>>>(ctf, kreal, C);
+  return cudaGetLastError();
+}
+static cudaError_t do_kreal(int N, const float4 *ctf, float4 *kreal, int C, cudaStream_t s)
+{
+  switch (N)
+  {
+#define X(n)                                                                                              \
+  case n:                                                                                                 \
+    return launch_kreal<n>(ctf, kreal, C, s);
+    BIOEM_SIZES(X)
+#undef X
+  }
+  return cudaErrorInvalidValue;
 }
 
 template <int N> static void geo_of(int *r1, int *r2)
@@ -405,8 +460,8 @@ static int set_ctf_priors(bioem_b200_context *h, const float *CtfParam4, int C)
   const int Cold = h->C;
   h->C = 0; // stays 0 (run() refuses) unless everything below succeeds
   h->state_ready = false;
-  if (C != Cold)
-    free_batch(h);
+  (void) Cold;
+  free_batch(h); // (also when C is unchanged: a real / complex table decides the mode of the fused kernel)
   RC(dev_realloc(h, h->d_prior, (size_t) C));
   CU(cudaMemcpyAsync(h->d_prior, prior.data(), sizeof(double) * C, cudaMemcpyHostToDevice, h->stream));
   CU(cudaStreamSynchronize(h->stream));
@@ -553,6 +608,7 @@ int bioem_b200_destroy(bioem_b200_handle h)
   dfree(h, h->d_dens);
   dfree(h, h->d_angles);
   dfree(h, h->d_ctf);
+  dfree(h, h->d_kreal);
   dfree(h, h->d_prior);
   dfree(h, h->d_refs);
   dfree(h, h->d_sumRef);
@@ -639,6 +695,23 @@ int bioem_b200_upload_ctf(bioem_b200_handle h, const float *refCTF, const float 
   RC(dev_realloc(h, h->d_ctf, h->map4 * C));
   CU(do_pack(N, tmp.as<float2>(), h->d_ctf, C, h->stream));
   h->launches++;
+  // CTFs computed in Fourier space are real (param.cpp:1540-1570): the fused kernel can then run in its
+  // cached-product mode, for which the real parts are laid out in column-pass order
+  bool real = true;
+  for (size_t i = 0; i < stdsz * C && real; i++)
+    real = refCTF[2 * i + 1] == 0.f;
+  h->ctf_is_real = false;
+  if (real)
+  {
+    size_t kr4 = 0;
+    int ctas = 0;
+    zgeo_for(N, 0, &kr4, &ctas);
+    h->kr4 = kr4;
+    RC(dev_realloc(h, h->d_kreal, kr4 * C));
+    CU(do_kreal(N, h->d_ctf, h->d_kreal, C, h->stream));
+    h->launches++;
+    h->ctf_is_real = true;
+  }
   CU(cudaStreamSynchronize(h->stream));
   h->C = Cold;
   return set_ctf_priors(h, CtfParam4, C);
@@ -659,6 +732,7 @@ int bioem_b200_upload_ctf_real(bioem_b200_handle h, const float *kernels, const 
   h->state_ready = false;
   const int Cold = h->C;
   h->C = 0;
+  h->ctf_is_real = false; // spectra of real-space kernels: complex in general
   RC(dev_realloc(h, h->d_ctf, h->map4 * C));
   CU(do_fft2d(N, img.as<float>(), nullptr, 0, 0.f, h->d_tw_fwd, scr.as<float2>(), h->d_ctf, C, h->stream));
   h->launches += 2;
@@ -844,11 +918,31 @@ static int ensure_batch(bioem_b200_context *h)
   RC(dev_realloc(h, h->d_tempden, (size_t) h->nbands * OB));
   RC(dev_realloc(h, h->d_scratch, (size_t) N * (N / 2 + 1) * OB));
   RC(dev_realloc(h, h->d_projfft, h->map4 * OB));
-  RC(dev_realloc(h, h->d_conv, h->map4 * (size_t) OB * h->C));
+  // Cached-product mode (real CTF tables): per orientation the fused kernel forms projection * conj(particle) once
+  // (about 0.12 likelihoods' worth of work) and saves about 5 % per likelihood -- worth it from 4 CTFs on.  The
+  // convolved spectra are then never formed: no OB x C conv maps in HBM (cfg 2: 1 GB), one scratch map per resident CTA.
+  bool zmode = h->ctf_is_real && h->d_kreal && h->C >= 4;
+  if (const char *v = getenv("BIOEM_B200_CACHED_PRODUCT"))
+    zmode = h->ctf_is_real && h->d_kreal && atoi(v) != 0;
+  if (zmode)
+  {
+    int dev_sms = 0, ctas = 0;
+    size_t kr4 = 0;
+    CU(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, h->device));
+    zgeo_for(N, smem_for(N, h->cfg.maxDisplaceCenter, h->nwp), &kr4, &ctas);
+    const int nslots = dev_sms * ctas;
+    RC(dev_realloc(h, h->d_zbuf, h->map4 * (size_t) nslots));
+    RC(dev_realloc(h, h->d_zflags, (size_t) nslots));
+    CU(cudaMemsetAsync(h->d_zflags, 0, sizeof(int) * (size_t) nslots, h->stream));
+    h->nslots = nslots;
+  }
+  // (in that mode only the inspection entry point debug_convolved wants convolved spectra: one orientation's worth)
+  RC(dev_realloc(h, h->d_conv, h->map4 * (size_t) (zmode ? 1 : OB) * h->C));
   RC(dev_realloc(h, h->d_cpar, (size_t) OB * h->C));
   h->partials_cap = (size_t) h->M * ((OB + h->OG - 1) / h->OG);
   RC(dev_realloc(h, h->d_partials, h->partials_cap));
   h->OB = OB;
+  h->zmode = zmode;
   return BIOEM_B200_OK;
 }
 
@@ -887,7 +981,7 @@ int bioem_b200_reset(bioem_b200_handle h)
 
 // stages 1 + 2 for orientations [o0, o0+OBcur) into the batch buffers
 static int run_front(bioem_b200_context *h, int o0, int OBcur, const float4 *angles = nullptr, const int4 *sel = nullptr,
-                     int nsel = 0)
+                     int nsel = 0, bool want_conv = false)
 {
   const int N = h->N;
   ProjParams pp;
@@ -913,7 +1007,8 @@ static int run_front(bioem_b200_context *h, int o0, int OBcur, const float4 *ang
   project_kernel<<<pg, h->proj_threads, (size_t) h->band_rows * N * 4, h->stream>>>(pp);
   CU(cudaGetLastError());
   CU(do_fft2d(N, h->d_proj, h->d_tempden, h->nbands, h->NormDen, h->d_tw_fwd, h->d_scratch, h->d_projfft, OBcur, h->stream));
-  CU(do_conv(N, h->d_projfft, h->d_ctf, h->d_prior, h->d_conv, h->d_cpar, h->C, OBcur, h->cfg.Ntotpi, h->stream, sel, nsel));
+  float4 *conv = (h->zmode && !want_conv) ? nullptr : h->d_conv; // (want_conv in cached-product mode: OBcur == 1)
+  CU(do_conv(N, h->d_projfft, h->d_ctf, h->d_prior, conv, h->d_cpar, h->C, OBcur, h->cfg.Ntotpi, h->stream, sel, nsel));
   h->launches += 4;
   return BIOEM_B200_OK;
 }
@@ -932,6 +1027,13 @@ static void fill_lik_params(bioem_b200_context *h, LikParams &lp, int o0, int OB
   lp.angles = h->cfg.writeAngles ? h->d_angtab : nullptr;
   lp.dbg_values = nullptr;
   lp.pairs = nullptr;
+  lp.projs = h->d_projfft;
+  lp.kreal = h->d_kreal;
+  lp.zbuf = h->d_zbuf;
+  lp.zflags = h->d_zflags;
+  lp.nslots = h->nslots;
+  lp.kr4 = (int) h->kr4;
+  lp.zmode = h->zmode ? 1 : 0;
   lp.M = h->M;
   lp.C = h->C;
   lp.OBcur = OBcur;
@@ -1544,6 +1646,13 @@ int bioem_b200_out_of_frame(bioem_b200_handle h, int *perOrient, long long *tota
   return BIOEM_B200_OK;
 }
 
+int bioem_b200_cached_product(bioem_b200_handle h)
+{
+  if (!h || h->OB <= 0)
+    return -1;
+  return h->zmode ? 1 : 0;
+}
+
 // ------------------------------------------------------------------ inspection
 int bioem_b200_debug_projection(bioem_b200_handle h, int o, float *out)
 {
@@ -1578,7 +1687,7 @@ int bioem_b200_debug_convolved(bioem_b200_handle h, int o, int c, float *conv_ou
   int rc = ensure_batch(h);
   if (rc)
     return rc;
-  rc = run_front(h, o, 1);
+  rc = run_front(h, o, 1, nullptr, nullptr, 0, true);
   if (rc)
     return rc;
   const size_t stdsz = (size_t) h->N * (h->N / 2 + 1);

@@ -629,7 +629,9 @@ __global__ void __launch_bounds__(NT) ctf_conv_kernel(const float4 *__restrict__
   const size_t oslot = sel ? (size_t) blockIdx.y : (size_t) ob * C + c;
   const float4 *P = proj + (size_t) ob * L::MAP4;
   const float4 *K = ctf + (size_t) c * L::MAP4;
-  float4 *V = conv + oslot * L::MAP4;
+  // (conv == nullptr: cached-product mode of the fused kernel, which never reads a convolved spectrum -- only
+  // sumC, sumsquareC and the displacement-independent term are needed)
+  float4 *V = conv ? conv + oslot * L::MAP4 : nullptr;
   float acc = 0.f;
   float sumC = 0.f;
   for (int i = tid; i < L::MAP4; i += NT)
@@ -649,7 +651,7 @@ __global__ void __launch_bounds__(NT) ctf_conv_kernel(const float4 *__restrict__
     if (tail || dc)
       w = 1.f;
     float4 vs = v;
-    if (tail || dc)
+    if (conv && (tail || dc))
     {
       // The reference's CTF table is not Hermitian along kx (quirk Q1), so neither is V in
       // the two self-conjugate columns ky = 0 and ky = N/2.  A c2r transform (FFTW) only sees
@@ -681,7 +683,8 @@ __global__ void __launch_bounds__(NT) ctf_conv_kernel(const float4 *__restrict__
       vs.z = 0.5f * (v.z + pv[2]);
       vs.w = 0.5f * (v.w - pv[3]);
     }
-    V[i] = vs;
+    if (conv)
+      V[i] = vs;
     acc += w * (v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w);
     if (i == 0)
       sumC = v.x; // kx = 0, ky = 0
@@ -723,6 +726,15 @@ struct LikParams
   // against conv spectrum b of the batch (launched with C = 1, OG = 1: the spectra were gathered per item);
   // its partial goes to partials[b], its correlation window to dbg_values[b]
   const int4 *pairs;
+  // cached-product mode (likelihood_kernel<N, W, true>, chosen by zmode != 0; needs REAL CTF kernels, i.e. CTFs given
+  // in Fourier space, param.cpp:1540-1570): conv * conj(particle) = (projection * conj(particle)) * K_c.  The CTA
+  // forms Z = projection * conj(particle) once per orientation into its private scratch map and streams Z and the
+  // real table K_c per CTF: 3/4 of the operand bytes and half of the multiplies of the complex path.
+  const float4 *projs; // [OBcur][MAP4] projection spectra of the batch
+  const float4 *kreal; // [C][kr4] real CTF tables in column-pass order (KLay<N>)
+  float4 *zbuf;        // [nslots][MAP4] scratch maps, one per resident CTA
+  int *zflags;         // [nslots] 0 = free
+  int nslots, kr4, zmode;
   int M, C, OBcur, OG, o_base;
   int nw;  // window points per axis
   int nwp; // nw rounded up to even
@@ -731,6 +743,75 @@ struct LikParams
   float ex2coef; // (3 - Nt)/2 * log2(e): sum of exp over the window runs in base 2
   double acoef_d;
 };
+
+// Real CTF table of the cached-product mode, per CTF, in the order the column pass consumes it: lane
+// (c, n2) of column chunk ch reads KQ float4 holding K(kx = n1*R2 + n2, ky = ch*KC + c) for n1 = 4q .. 4q+3 at
+// [(ch*KQ + q)*KC*R2 + lane]; the Nyquist column follows as [MAINK4 + q*R2 + n2].  The two self-conjugate columns
+// ky = 0 and N/2 hold (K(kx) + K(N-kx))/2: the c2r transform only sees the Hermitian part of these columns
+// (quirk Q1, see ctf_conv_kernel), and for Hermitian projection / particle columns that part is Z * K_sym.
+template <int N> struct KLay
+{
+  using L = Lay<N>;
+  static constexpr int KQ = (L::R1 + 3) / 4;
+  static constexpr int KCR2 = L::KC * L::R2;
+  static constexpr int MAINK4 = L::NCH * KQ * KCR2;
+  static constexpr int KR4 = MAINK4 + KQ * L::R2;
+};
+
+#ifndef BIOEM_LIK_ONLY
+template <int N>
+__global__ void kreal_kernel(const float4 *__restrict__ ctf, float4 *__restrict__ kreal, int C)
+{
+  using L = Lay<N>;
+  using K = KLay<N>;
+  const int c = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K::KR4 || c >= C)
+    return;
+  const float4 *T = ctf + (size_t) c * L::MAP4;
+  int ch, q, n2, kyl;
+  const bool tail = i >= K::MAINK4;
+  if (!tail)
+  {
+    const int lane = i % K::KCR2;
+    q = (i / K::KCR2) % K::KQ;
+    ch = i / (K::KCR2 * K::KQ);
+    kyl = lane / L::R2;
+    n2 = lane % L::R2;
+  }
+  else
+  {
+    const int t = i - K::MAINK4;
+    n2 = t % L::R2;
+    q = t / L::R2;
+    ch = 0;
+    kyl = 0;
+  }
+  // real part of the table at (kx, this column)
+  auto at = [&](int kx) {
+    const int n1 = kx / L::R2, m2 = kx % L::R2;
+    const float4 v = T[tail ? L::MAIN4 + (n1 / 2) * L::R2 + m2 : L::main_idx(ch, n1 / 2, m2, kyl)];
+    return (n1 & 1) ? v.z : v.x;
+  };
+  const bool selfconj = tail || (ch == 0 && kyl == 0);
+  float out[4];
+#pragma unroll
+  for (int e = 0; e < 4; e++)
+  {
+    const int n1 = 4 * q + e;
+    float v = 0.f;
+    if (n1 < L::R1)
+    {
+      const int kx = n1 * L::R2 + n2;
+      v = at(kx);
+      if (selfconj)
+        v = 0.5f * (v + at((N - kx) % N));
+    }
+    out[e] = v;
+  }
+  kreal[(size_t) c * K::KR4 + i] = make_float4(out[0], out[1], out[2], out[3]);
+}
+#endif
 
 // number of leading (= trailing) radix-R2 output groups that can hold a displacement of
 // [-maxD, maxD]: raw index k = k1 + R1*k2, k <= maxD or k >= N - maxD
@@ -924,9 +1005,10 @@ struct BookState
 // -> rows) and one split-phase mbarrier (rows -> next columns: arrive, run the first radix pass
 // of the next likelihood's first chunk, wait); no correlation map ever leaves the SM.
 // ===========================================================================
-template <int N, int W>
+template <int N, int W, bool ZM>
 __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXREG) likelihood_kernel(LikParams p)
 {
+  using KL = KLay<N>;
   using L = Lay<N>;
   using SM = LikSmem<N>;
   constexpr int NK = SM::nk(W); // radix-R2 output groups kept
@@ -961,9 +1043,26 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
   __shared__ int s_poc[NPEND];
   __shared__ unsigned long long s_mbar; // closing barrier of a likelihood (one arrival per warp)
   __shared__ BookState s_bk;
+  __shared__ int s_zslot;
 
   const int nw = p.nw, nwp = p.nwp;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x;
+  int warp = tid >> 5;
+  int lane = tid & 31;
+  // (cached-product variant: with one more operand stream the register allocator sits at its 128-register cap and
+  // would rather re-derive the lane number from the thread-id register inside every column task -- a long-latency
+  // S2R in front of the operand loads -- than keep it; an opaque move makes it keep it)
+#ifndef BIOEM_ZV
+#define BIOEM_ZV 27
+#endif
+  // (measured at N = 224, ns per likelihood: none 46.2, lane 45.9, + scratch offset 45.6, + table offset 45.4,
+  // + warp number 45.1; the same moves make the complex-path kernel spill, so they are this variant's only)
+  constexpr int RV = ZM ? BIOEM_ZV : 0;
+  constexpr bool LATE_SUMS = (RV & 4) != 0;
+  if constexpr ((RV & 1) != 0)
+    asm volatile("" : "+r"(lane));
+  if constexpr ((RV & 16) != 0)
+    asm volatile("" : "+r"(warp));
   float2 *E = Eall + (size_t) warp * SM::EW;
   const int m = p.pairs ? p.pairs[blockIdx.x].x : blockIdx.x % p.M;
   const int g = p.pairs ? blockIdx.x : blockIdx.x / p.M;
@@ -1001,8 +1100,27 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
     s_bk.lpf = 0.f;
     s_bk.v = s_bk.sC = s_bk.ssC = 0.f;
     s_bk.o = s_bk.c = s_bk.lin = 0;
+    if constexpr (ZM)
+    {
+      // a private scratch map for this CTA's cached product: first free slot, starting at this SM's own (there are as
+      // many slots as CTAs can be resident, so the search ends at once; it would also end with fewer)
+      unsigned smid, nsm;
+      asm("mov.u32 %0, %%smid;" : "=r"(smid));
+      asm("mov.u32 %0, %%nsmid;" : "=r"(nsm));
+      const unsigned per_sm = max(1u, (unsigned) p.nslots / max(1u, nsm));
+      int sl = (int) ((smid * per_sm) % (unsigned) p.nslots);
+      while (atomicCAS(p.zflags + sl, 0, 1) != 0)
+        sl = sl + 1 == p.nslots ? 0 : sl + 1;
+      s_zslot = sl;
+    }
   }
   __syncthreads();
+  float4 *zs = ZM ? p.zbuf + (size_t) s_zslot * L::MAP4 : nullptr;
+  // this lane's float4 of column chunk 0 in the scratch maps (kept, not re-derived, for the same reason)
+  int zoff = ZM ? s_zslot * L::MAP4 + lane : 0;
+  if constexpr (ZM && (BIOEM_ZV & 2))
+    asm volatile("" : "+r"(zoff));
+  float4 *const zs_l = p.zbuf + zoff;
 
   // lane roles (fixed for the whole kernel).  Pass 1 of both transforms: lane = c*R2 + n2
   // (c = column / row pair within the warp's task, n2 = sub-sequence).  Pass 2: item = k1*KC + c.
@@ -1056,7 +1174,20 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
   // loads and multiplies again) goes to the last warp, which has the fewest row tasks: its first
   // radix pass runs in that warp's slack before the closing barrier.
   const int ch0 = (warp + 1) % NWARP;
-  const float sR = p.sumRef[m], ssR = p.sumsqRef[m];
+  // (the particle's sums and the conv spectrum's sums are only needed in the row pass: they are read there, behind
+  // the column -> row barrier, instead of living in registers through the column pass, where every register counts)
+  __shared__ float s_sr[2];
+  float sR0 = 0.f, ssR0 = 0.f;
+  if constexpr (LATE_SUMS)
+  {
+    if (tid == 0)
+    {
+      s_sr[0] = p.sumRef[m];
+      s_sr[1] = p.sumsqRef[m];
+    }
+  }
+  else
+    sR0 = p.sumRef[m], ssR0 = p.sumsqRef[m];
   const float Nt = p.Ntotpi;
   int slot = 0; // likelihoods in the ring (uniform over the CTA)
 
@@ -1156,8 +1287,105 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
   };
 #endif
   // (more: another likelihood follows the one conv belongs to -- only the staging variant needs to know)
+  // the radix-R1 butterflies, the inter-pass twiddles and the store into the warp's exchange tile
+  auto col1_finish = [&](float2(&x)[R1]) {
+    bfft::Dft<R1, 1>::run(x);
+#pragma unroll
+    for (int k1 = 1; k1 < R1; k1++)
+      x[k1] = bfft::cmul(x[k1], tw[k1]);
+#pragma unroll
+    for (int k1 = 0; k1 < R1; k1++)
+      E[k1 * ES + a_c * CS + a_n2] = x[k1];
+  };
+  // Cached-product mode: Z = projection * conj(particle) of the current orientation, this warp's column chunks, into
+  // the CTA's scratch map.  Every lane later reads back exactly the float4 it stored here (same chunk -> warp -> lane
+  // assignment as col1), so the scratch needs no synchronisation at all; it stays in L2.
+  auto zpass = [&](int pidx) {
+    if constexpr (ZM)
+    {
+      const float4 *P = p.projs + (size_t) pidx * L::MAP4;
+      if (a_act)
+      {
+        for (int ch = ch0; ch < NCH; ch += NWARP)
+        {
+          const int base = ch * (R1 / 2) * KC * R2 + lane;
+#pragma unroll
+          for (int n1p = 0; n1p < R1 / 2; n1p++)
+          {
+            const float4 r = ldg4(ref + base + n1p * KC * R2);
+            const float4 v = ldg4(P + base + n1p * KC * R2);
+            const float2 za = bfft::cmulc(make_float2(v.x, v.y), make_float2(r.x, r.y));
+            const float2 zb = bfft::cmulc(make_float2(v.z, v.w), make_float2(r.z, r.w));
+            zs_l[base - lane + n1p * KC * R2] = make_float4(za.x, za.y, zb.x, zb.y);
+          }
+          if (ch == 0 && a_c == 0)
+          {
+#pragma unroll
+            for (int n1p = 0; n1p < R1 / 2; n1p++)
+            {
+              const float4 r = ldg4(ref + L::MAIN4 + n1p * R2 + a_n2);
+              const float4 v = ldg4(P + L::MAIN4 + n1p * R2 + a_n2);
+              const float2 za = bfft::cmulc(make_float2(v.x, v.y), make_float2(r.x, r.y));
+              const float2 zb = bfft::cmulc(make_float2(v.z, v.w), make_float2(r.z, r.w));
+              zs[L::MAIN4 + n1p * R2 + a_n2] = make_float4(za.x, za.y, zb.x, zb.y);
+            }
+          }
+        }
+      }
+      __syncwarp();
+    }
+  };
+  // (conv: the conv spectrum of the likelihood -- in cached-product mode the real table of its CTF)
   auto col1_ = [&](int ch, const float4 *conv, bool more, auto first_) {
     constexpr bool FIRST = decltype(first_)::value;
+    if constexpr (ZM)
+    {
+      if (a_act)
+      {
+        float2 x[R1];
+        const int base = ch * (R1 / 2) * KC * R2; // (+ lane: in zs_l)
+        float kk[4 * KL::KQ];
+#pragma unroll
+        for (int q = 0; q < KL::KQ; q++)
+        {
+          const float4 k4 = ldg4(conv + (ch * KL::KQ + q) * KL::KCR2 + lane);
+          kk[4 * q] = k4.x, kk[4 * q + 1] = k4.y, kk[4 * q + 2] = k4.z, kk[4 * q + 3] = k4.w;
+        }
+#pragma unroll
+        for (int n1p = 0; n1p < R1 / 2; n1p++)
+        {
+          const float4 z = zs_l[base + n1p * KC * R2];
+          x[2 * n1p] = __fmul2_rn(make_float2(z.x, z.y), make_float2(kk[2 * n1p], kk[2 * n1p]));
+          x[2 * n1p + 1] = __fmul2_rn(make_float2(z.z, z.w), make_float2(kk[2 * n1p + 1], kk[2 * n1p + 1]));
+        }
+        if constexpr (FIRST)
+        {
+          if (a_c == 0)
+          {
+            // pack the Nyquist column into the (Hermitian) DC column: Z = X0 + i*X_{N/2}
+            float kt[4 * KL::KQ];
+#pragma unroll
+            for (int q = 0; q < KL::KQ; q++)
+            {
+              const float4 k4 = ldg4(conv + KL::MAINK4 + q * R2 + a_n2);
+              kt[4 * q] = k4.x, kt[4 * q + 1] = k4.y, kt[4 * q + 2] = k4.z, kt[4 * q + 3] = k4.w;
+            }
+#pragma unroll
+            for (int n1p = 0; n1p < R1 / 2; n1p++)
+            {
+              const float4 z = zs[L::MAIN4 + n1p * R2 + a_n2];
+              x[2 * n1p] = bfft::cadd_i(x[2 * n1p], __fmul2_rn(make_float2(z.x, z.y), make_float2(kt[2 * n1p], kt[2 * n1p])));
+              x[2 * n1p + 1] =
+                bfft::cadd_i(x[2 * n1p + 1], __fmul2_rn(make_float2(z.z, z.w), make_float2(kt[2 * n1p + 1], kt[2 * n1p + 1])));
+            }
+          }
+        }
+        col1_finish(x);
+      }
+      __syncwarp();
+    }
+    else
+    {
 #ifdef BIOEM_TMA
     {
       unsigned done;
@@ -1232,15 +1460,10 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
           }
         }
       }
-      bfft::Dft<R1, 1>::run(x);
-#pragma unroll
-      for (int k1 = 1; k1 < R1; k1++)
-        x[k1] = bfft::cmul(x[k1], tw[k1]);
-#pragma unroll
-      for (int k1 = 0; k1 < R1; k1++)
-        E[k1 * ES + a_c * CS + a_n2] = x[k1];
+      col1_finish(x);
     }
     __syncwarp();
+    }
   };
   auto col1 = [&](int ch, const float4 *conv, bool more) {
     if (ch == 0)
@@ -1311,6 +1534,8 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
   if (o_lo < o_hi)
     tma_issue(ch0, p.convs + (size_t) o_lo * p.C * L::MAP4);
 #endif
+  if (o_lo < o_hi)
+    zpass(p.pairs ? p.pairs[blockIdx.x].y : o_lo);
   for (int ol = o_lo; ol < o_hi; ol++)
   {
     if (tid == 0)
@@ -1321,21 +1546,18 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
     for (int c = 0; c < p.C; c++)
     {
       const int oc = ol * p.C + c;
-      const float4 *conv = p.convs + (size_t) oc * L::MAP4;
-      const ConvParam cp = p.cpar[oc];
+      // (cached-product mode: the real table of CTF c, or of the work item's CTF)
+      int koff = ZM ? (p.pairs ? p.pairs[blockIdx.x].z : c) * p.kr4 : 0;
+      if constexpr (ZM && (BIOEM_ZV & 8))
+        asm volatile("" : "+r"(koff));
+      const float4 *conv = ZM ? p.kreal + koff : p.convs + (size_t) oc * L::MAP4;
       if (tid == 0)
         s_poc[slot] = oc;
-      // firstele = Nt*(ssR*ssC - v*v) + 2*sR*sC*v - ssR*sC*sC - sR*sR*ssC   (FP32, source order)
-      const float f_a = __fmul_rn(ssR, cp.sumsqC);
-      const float f_b = __fmul_rn(__fmul_rn(2.f, sR), cp.sumC);
-      const float f_c = __fmul_rn(__fmul_rn(ssR, cp.sumC), cp.sumC);
-      const float f_d = __fmul_rn(__fmul_rn(sR, sR), cp.sumsqC);
-      float mfd[AMASK ? P2 * NK : 1];
-      if constexpr (AMASK)
+      float sumC, sumsqC;
+      if constexpr (!LATE_SUMS)
       {
-#pragma unroll
-        for (int q = 0; q < P2 * NK; q++)
-          mfd[q] = ((vmask >> q) & 1u) ? -f_d : FE_INVALID;
+        const ConvParam cp = p.cpar[oc];
+        sumC = cp.sumC, sumsqC = cp.sumsqC;
       }
 
       // ------------------------------------------------ column pass (along kx), per warp
@@ -1347,6 +1569,22 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
       }
       pre_done = false;
       __syncthreads(); // all candidate rows of all columns are in Y
+      // firstele = Nt*(ssR*ssC - v*v) + 2*sR*sC*v - ssR*sC*sC - sR*sR*ssC   (FP32, source order)
+      // (the loads are issued here; their values are first needed in the epilogue of the first row task)
+      if constexpr (LATE_SUMS)
+        sumC = __ldg(&p.cpar[oc].sumC), sumsqC = __ldg(&p.cpar[oc].sumsqC);
+      const float sR = LATE_SUMS ? s_sr[0] : sR0, ssR = LATE_SUMS ? s_sr[1] : ssR0;
+      const float f_a = __fmul_rn(ssR, sumsqC);
+      const float f_b = __fmul_rn(__fmul_rn(2.f, sR), sumC);
+      const float f_c = __fmul_rn(__fmul_rn(ssR, sumC), sumC);
+      const float f_d = __fmul_rn(__fmul_rn(sR, sR), sumsqC);
+      float mfd[AMASK ? P2 * NK : 1];
+      if constexpr (AMASK)
+      {
+#pragma unroll
+        for (int q = 0; q < P2 * NK; q++)
+          mfd[q] = ((vmask >> q) & 1u) ? -f_d : FE_INVALID;
+      }
 
       // ------------------------------------------------ row pass (along ky), 2 rows per transform
       // running minimum of firstele of this thread, its enumeration index and correlation value,
@@ -1516,7 +1754,17 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
         asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(mbar_addr) : "memory");
       if (ch0 < NCH && oc + 1 < o_hi * p.C)
       {
-        col1(ch0, conv + L::MAP4, oc + 2 < o_hi * p.C); // the next conv spectrum of the batch follows this one
+        if constexpr (ZM)
+        {
+          // the next CTF's table follows this one; after the last CTF the next orientation's product comes first
+          // (it, too, needs neither Y nor the other warps)
+          const bool last = c == p.C - 1;
+          if (last)
+            zpass(ol + 1);
+          col1(ch0, last ? p.kreal : conv + p.kr4, false);
+        }
+        else
+          col1(ch0, conv + L::MAP4, oc + 2 < o_hi * p.C); // the next conv spectrum of the batch follows this one
         pre_done = true;
       }
       {
@@ -1565,6 +1813,10 @@ __global__ void __launch_bounds__(LikSmem<N>::LNT) __maxnreg__(LikSmem<N>::MAXRE
     r.sumsqC = s_bk.ssC;
     r.pad = 0;
     p.partials[p.pairs ? (size_t) blockIdx.x : (size_t) g * p.M + m] = r;
+    // (every warp is past its last read of the scratch map: their arrivals at the closing barrier of the last
+    // likelihood came after their column passes)
+    if constexpr (ZM)
+      atomicExch(p.zflags + s_zslot, 0);
   }
 }
 

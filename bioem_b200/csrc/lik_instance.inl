@@ -5,15 +5,20 @@
 
 namespace bioem
 {
-template <int W> static cudaError_t lik_launch_w(const LikParams &p, int nblocks, cudaStream_t s)
+template <int W, bool ZM> static cudaError_t lik_launch_wz(const LikParams &p, int nblocks, cudaStream_t s)
 {
   const size_t smem = LikSmem<BIOEM_N>::bytes(W, p.nwp);
   // attribute is per device context: set on every launch (cheap next to the kernel)
-  cudaError_t e = cudaFuncSetAttribute(likelihood_kernel<BIOEM_N, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+  cudaError_t e = cudaFuncSetAttribute(likelihood_kernel<BIOEM_N, W, ZM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
   if (e != cudaSuccess)
     return e;
-  likelihood_kernel<BIOEM_N, W><<<nblocks, LikSmem<BIOEM_N>::LNT, smem, s>>>(p);
+  likelihood_kernel<BIOEM_N, W, ZM><<<nblocks, LikSmem<BIOEM_N>::LNT, smem, s>>>(p);
   return cudaGetLastError();
+}
+// p.zmode selects the cached-product variant (real CTF tables, LikParams::projs / kreal / zbuf)
+template <int W> static cudaError_t lik_launch_w(const LikParams &p, int nblocks, cudaStream_t s)
+{
+  return p.zmode ? lik_launch_wz<W, true>(p, nblocks, s) : lik_launch_wz<W, false>(p, nblocks, s);
 }
 } // namespace bioem
 

@@ -215,6 +215,14 @@ int bioem_b200_kernel_time(bioem_b200_handle h, double *likelihood_ms, long long
  * (perOrient[nOrient], may be NULL) and in total. */
 int bioem_b200_out_of_frame(bioem_b200_handle h, int *perOrient, long long *total);
 
+/* Mode of the fused kernel for the inputs now on the handle: 1 = cached-product mode (every CTF kernel is real,
+ * i.e. computed in Fourier space as param.cpp:1540-1570 does, and there are at least 4 of them: the product
+ * projection * conj(particle) is formed once per orientation and multiplied by the real kernels), 0 = complex
+ * convolved spectra (USE_PSF, few CTFs), -1 = not decided yet (decided by the first run() after the uploads).
+ * The results of the two modes differ by FP32 rounding only (multiplication order).
+ * BIOEM_B200_CACHED_PRODUCT=0/1 in the environment overrides the choice for real kernels. */
+int bioem_b200_cached_product(bioem_b200_handle h);
+
 /* ---- inspection entry points (tests): intermediate products of one orientation ---- */
 /* real-space projection (N*N, already scaled by NormDen/tempden) */
 int bioem_b200_debug_projection(bioem_b200_handle h, int iOrient, float *proj_out);

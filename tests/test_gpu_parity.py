@@ -428,6 +428,53 @@ def test_uploads_invalidate_the_running_state(setups):
         fresh.close()
 
 
+@pytest.mark.parametrize("name", ["toy64", "cfg2_slice", "cfg4_voxel_slice"])
+def test_cached_product_mode_agrees_with_complex_mode(monkeypatch, setups, name):
+    """Real CTF kernels (Fourier-space CTFs, >= 4 of them) make the fused kernel form projection * conj(particle) once per
+    orientation and multiply by the real kernels (bioem_b200_cached_product == 1); the complex path multiplies the
+    convolved spectrum by conj(particle).  Same arithmetic up to the order of two FP32 multiplications: log P agrees to
+    2e-6 relative (a tenth of the tolerance against the oracle), the arg-max records are the same (or tie in float-narrowed log-posterior), and the convolved
+    spectrum is still available to the inspection entry point."""
+    cd, hi, parts, eng, P = setups(name)
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("BIOEM_B200_CACHED_PRODUCT", mode)
+        e = _engine_with(hi, parts)
+        try:
+            e.run()
+            pm, _ = e.download()
+            assert e.cached_product() == int(mode)
+            assert e.exact_argmax_info()[2] == 0
+            conv, sC, ssC = e.debug_convolved(hi.O - 1, hi.C - 1)
+            res[mode] = (pm, conv, sC, ssC)
+        finally:
+            e.close()
+    monkeypatch.delenv("BIOEM_B200_CACHED_PRODUCT")
+    a, b = res["1"][0], res["0"][0]
+    logp = lambda r: np.log(r["Total"]) + r["Constoadd"]
+    np.testing.assert_allclose(logp(a), logp(b), rtol=2e-6, atol=0.1 * LOGP_ATOL[hi.N])
+    same = (a["orient"] == b["orient"]) & (a["conv"] == b["conv"]) & (a["cent_x"] == b["cent_x"]) & (a["cent_y"] == b["cent_y"])
+    assert np.all(same | (np.abs(a["Constoadd"] - b["Constoadd"]) <= NEAR_TIE[hi.N]))
+    # stage 2 does not depend on the mode
+    np.testing.assert_array_equal(res["1"][1], res["0"][1])
+    assert res["1"][2:] == res["0"][2:]
+    # default choice: cached product for these tables
+    e = _engine_with(hi, parts)
+    try:
+        e.run(0, 1)
+        assert e.cached_product() == (1 if hi.C >= 4 else 0)
+    finally:
+        e.close()
+
+
+def test_psf_kernels_use_the_complex_path(setups):
+    cd, hi, parts, eng, P = setups("toy32psf")
+    assert eng.cached_product() in (-1, 0)
+    eng.reset()
+    eng.run(0, 1)
+    assert eng.cached_product() == 0
+
+
 def test_out_of_frame_points_are_counted(setups):
     """reference bioem.cpp:1724-1734,1756-1780: model points that leave the frame are skipped with a warning;
     the library reports how many per orientation."""
