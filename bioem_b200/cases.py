@@ -102,6 +102,11 @@ CASES = {
                  particle_format="mrc", bulk_particles=1000),
     # DISPLACE_CENTER whose spacing does not divide the maximum displacement: Algo 1 enumerates 0,2,4 and
     # N-5,N-3,N-1 (3 + 3 points per axis), not a symmetric set (quirk Q3, bioem_algorithm.h:156-197)
+    # image edges without a fused FFT kernel (direct-DFT path of the library): odd, odd with a displacement grid and
+    # WRITE_PROB_ANGLES, even with a prime factor above 7
+    "toy33": Case("toy33", 33, 1.5, 60, 3, 576, 12, CFG1_CTF, 4, 1, model_sigma=5.0, model_rmax=12.0),
+    "toy35g2": Case("toy35g2", 35, 1.5, 60, 3, 576, 10, CFG1_CTF, 5, 2, write_angles=2, model_sigma=5.0, model_rmax=12.0),
+    "toy26": Case("toy26", 26, 1.5, 60, 3, 576, 12, CFG1_CTF, 3, 1, model_sigma=4.0, model_rmax=10.0),
     "toy32g2odd": Case("toy32g2odd", 32, 1.5, 60, 3, 576, 12, CFG1_CTF, 5, 2, model_sigma=5.0, model_rmax=12.0),
     "toy32g3": Case("toy32g3", 32, 1.5, 60, 3, 576, 12, CFG1_CTF, 7, 3, write_angles=2, model_sigma=5.0, model_rmax=12.0),
     # BASELINE.json configs[3] at its named shape: 48^3 MRC density volume (110,592 points of radius 2 px) read with

@@ -1,6 +1,7 @@
 // Context, batching and the device half of the C ABI (include/bioem_b200.h).
 #include "../../include/bioem_b200.h"
 #include "bioem_kernels.cuh"
+#include "generic_kernels.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -105,6 +106,11 @@ struct bioem_b200_context
   // cached-product mode of the fused kernel (LikParams::zmode): possible when every CTF kernel is real (CTFs given
   // in Fourier space), chosen in ensure_batch
   bool ctf_is_real = false, zmode = false;
+  // direct-DFT path (generic_kernels.cuh) for image edges without an instantiated fused kernel: spectra in the
+  // reference's layout, correlation windows of a batch in d_values, window displacements in d_wl
+  bool generic = false;
+  int *d_wl = nullptr;
+  float *d_values = nullptr;
   float4 *d_kreal = nullptr; // [C][kr4] real tables in column-pass order
   float4 *d_zbuf = nullptr;  // [nslots][map4] scratch maps of the resident CTAs
   int *d_zflags = nullptr;
@@ -219,6 +225,8 @@ static void free_batch(bioem_b200_context *h)
   dfree(h, h->d_partials);
   dfree(h, h->d_zbuf);
   dfree(h, h->d_zflags);
+  dfree(h, h->d_values);
+  h->d_values = nullptr;
   h->d_zbuf = nullptr;
   h->d_zflags = nullptr;
   h->nslots = 0;
@@ -290,6 +298,10 @@ static cudaError_t do_kreal(int N, const float4 *ctf, float4 *kreal, int C, cuda
   return cudaErrorInvalidValue;
 }
 
+// float4 per map on the direct-DFT path: N x (N/2+1) complex in the reference's layout, rounded up to whole float4
+static size_t map4_generic(int N) { return ((size_t) N * (N / 2 + 1) + 1) / 2; }
+static bool is_generic(int N) { return map4_for(N) == 0; }
+
 template <int N> static void geo_of(int *r1, int *r2)
 {
   *r1 = Lay<N>::R1;
@@ -354,6 +366,12 @@ template <int N> static size_t lik_smem(int maxD, int nwp)
 
 static cudaError_t do_pack(int N, const float2 *src, float4 *dst, int nmaps, cudaStream_t s)
 {
+  if (is_generic(N)) // the reference's layout is the device layout: a strided copy
+  {
+    const size_t F = (size_t) N * (N / 2 + 1);
+    return cudaMemcpy2DAsync(dst, map4_generic(N) * sizeof(float4), src, F * sizeof(float2), F * sizeof(float2), nmaps,
+                             cudaMemcpyDeviceToDevice, s);
+  }
   switch (N)
   {
 #define X(n)                                                                                              \
@@ -366,6 +384,12 @@ static cudaError_t do_pack(int N, const float2 *src, float4 *dst, int nmaps, cud
 }
 static cudaError_t do_unpack(int N, const float4 *src, float2 *dst, int nmaps, cudaStream_t s)
 {
+  if (is_generic(N))
+  {
+    const size_t F = (size_t) N * (N / 2 + 1);
+    return cudaMemcpy2DAsync(dst, F * sizeof(float2), src, map4_generic(N) * sizeof(float4), F * sizeof(float2), nmaps,
+                             cudaMemcpyDeviceToDevice, s);
+  }
   switch (N)
   {
 #define X(n)                                                                                              \
@@ -379,6 +403,17 @@ static cudaError_t do_unpack(int N, const float4 *src, float2 *dst, int nmaps, c
 static cudaError_t do_fft2d(int N, const float *imgs, const double *tempden, int nbands, float normDen, const float2 *tw,
                             float2 *scratch, float4 *packed, int nimg, cudaStream_t s)
 {
+  if (is_generic(N))
+  {
+    // (tw: exp(+2 pi i j / N) on this path, for both directions)
+    gen_dft_rows_kernel<<<dim3(N, nimg), 256, (size_t) N * 12, s>>>(imgs, tempden, nbands, normDen, tw, N, scratch);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess)
+      return e;
+    gen_dft_cols_kernel<<<dim3(N, nimg), 256, (size_t) N * 8, s>>>(scratch, tw, N, 2 * map4_generic(N),
+                                                                    reinterpret_cast<float2 *>(packed));
+    return cudaGetLastError();
+  }
   switch (N)
   {
 #define X(n)                                                                                              \
@@ -392,6 +427,14 @@ static cudaError_t do_fft2d(int N, const float *imgs, const double *tempden, int
 static cudaError_t do_conv(int N, const float4 *proj, const float4 *ctf, const double *prior, float4 *conv, ConvParam *cpar,
                            int C, int OBcur, float Nt, cudaStream_t s, const int4 *sel = nullptr, int nsel = 0)
 {
+  if (is_generic(N))
+  {
+    if (sel || !conv)
+      return cudaErrorInvalidValue; // (no exact arg-max pass, no cached-product mode on this path)
+    gen_conv_kernel<<<dim3(C, OBcur), 256, 0, s>>>(reinterpret_cast<const float2 *>(proj), reinterpret_cast<const float2 *>(ctf),
+                                                   prior, reinterpret_cast<float2 *>(conv), cpar, C, N, 2 * map4_generic(N), Nt);
+    return cudaGetLastError();
+  }
   switch (N)
   {
 #define X(n)                                                                                              \
@@ -418,8 +461,12 @@ static cudaError_t do_lik(int N, const LikParams &p, int nblocks, int maxD, cuda
   }
   return cudaErrorInvalidValue;
 }
+// dynamic shared memory of gen_corr_kernel: twiddles, T[nw][N/2+1], window list
+static size_t gen_corr_smem(int N, int nw) { return ((size_t) N + (size_t) nw * (N / 2 + 1)) * sizeof(float2) + (size_t) nw * 4; }
 static size_t smem_for(int N, int maxD, int nwp)
 {
+  if (is_generic(N))
+    return gen_corr_smem(N, nwp) + 64;
   switch (N)
   {
 #define X(n)                                                                                              \
@@ -514,6 +561,24 @@ static int create_impl(bioem_b200_context *h, const bioem_b200_config *cfg)
   int R1 = 0, R2 = 0;
   geo_for(N, &R1, &R2);
   std::vector<float2> twi(N), twf(N);
+  if (h->generic)
+  {
+    // direct-DFT path: one table exp(+2 pi i j / N) for both directions, and the window displacements in
+    // enumeration order (the inverse of the window table below)
+    for (int j = 0; j < N; j++)
+    {
+      const double ang = 2.0 * M_PI * (double) j / (double) N;
+      twi[j] = twf[j] = make_float2((float) cos(ang), (float) sin(ang));
+    }
+    std::vector<int> wl(h->nw);
+    for (int k = 0; k < h->npos; k++)
+      wl[k] = k * cfg->GridSpaceCenter;
+    for (int k = 0; k < h->nw - h->npos; k++)
+      wl[h->npos + k] = N - cfg->maxDisplaceCenter + k * cfg->GridSpaceCenter;
+    RC(dev_realloc(h, h->d_wl, (size_t) h->nw));
+    CU(cudaMemcpyAsync(h->d_wl, wl.data(), sizeof(int) * h->nw, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+  }
   for (int n2 = 0; n2 < R2; n2++)
     for (int k1 = 0; k1 < R1; k1++)
     {
@@ -545,8 +610,10 @@ int bioem_b200_create(const bioem_b200_config *cfg, int device, bioem_b200_handl
     return fail(BIOEM_B200_ERR_INVALID, "null argument");
   *out = nullptr;
   const int N = cfg->NumberPixels;
-  if (!bioem_b200_supported_size(N))
-    return fail(BIOEM_B200_ERR_INVALID, "NUMBER_PIXELS " + std::to_string(N) + " is not an instantiated image edge");
+  // (edges without an instantiated fused kernel -- odd, prime factors above 7, above 512 -- run on the direct-DFT
+  // path; the reference accepts any edge, param.cpp:140-152)
+  if (N < 2 || N > 4096)
+    return fail(BIOEM_B200_ERR_INVALID, "NUMBER_PIXELS " + std::to_string(N) + " is out of range (2..4096)");
   if (cfg->GridSpaceCenter < 1 || cfg->maxDisplaceCenter < 0)
     return fail(BIOEM_B200_ERR_INVALID, "DISPLACE_CENTER: grid spacing must be >= 1 and the maximum displacement >= 0");
   if (2 * cfg->maxDisplaceCenter + 1 > N)
@@ -573,7 +640,8 @@ int bioem_b200_create(const bioem_b200_config *cfg, int device, bioem_b200_handl
   h->npos = npos;
   h->nw = nw;
   h->nwp = nw + (nw & 1);
-  h->map4 = map4_for(N);
+  h->generic = is_generic(N);
+  h->map4 = h->generic ? map4_generic(N) : map4_for(N);
   h->time_kernels = getenv("BIOEM_B200_KERNEL_TIMING") != nullptr && atoi(getenv("BIOEM_B200_KERNEL_TIMING")) != 0;
   const int rc = create_impl(h, cfg);
   if (rc != BIOEM_B200_OK)
@@ -616,6 +684,7 @@ int bioem_b200_destroy(bioem_b200_handle h)
   dfree(h, h->d_tw_inv);
   dfree(h, h->d_tw_fwd);
   dfree(h, h->d_wtab);
+  dfree(h, h->d_wl);
   dfree(h, h->d_state);
   dfree(h, h->d_angtab);
   dfree(h, h->d_out);
@@ -701,7 +770,7 @@ int bioem_b200_upload_ctf(bioem_b200_handle h, const float *refCTF, const float 
   for (size_t i = 0; i < stdsz * C && real; i++)
     real = refCTF[2 * i + 1] == 0.f;
   h->ctf_is_real = false;
-  if (real)
+  if (real && !h->generic)
   {
     size_t kr4 = 0;
     int ctas = 0;
@@ -879,6 +948,13 @@ static int ensure_batch(bioem_b200_context *h)
   ob = std::max<long>(1, std::min<long>(ob, h->O));
   if (env_pos("BIOEM_B200_OB"))
     ob = std::max<long>(1, std::min<long>(env_pos("BIOEM_B200_OB"), h->O));
+  if (h->generic)
+  {
+    // direct-DFT path: the correlation windows of a batch go through HBM (same budget), one grid row per conv spectrum
+    const size_t per_o = (size_t) h->C * h->M * h->nw * h->nw * sizeof(float);
+    ob = std::max<long>(1, std::min<long>(ob, (long) (budget / std::max<size_t>(per_o, 1))));
+    ob = std::max<long>(1, std::min<long>(ob, 65535 / std::max(1, h->C)));
+  }
   h->OB = (int) ob;
   // orientations per CTA: amortise the CTA prologue (and the one likelihood per CTA whose first radix pass
   // cannot be run ahead) over >= 64 likelihoods, keep >= 4 waves (cfg2: 1 -> 2 orientations, +0.5 %)
@@ -924,6 +1000,11 @@ static int ensure_batch(bioem_b200_context *h)
   bool zmode = h->ctf_is_real && h->d_kreal && h->C >= 4;
   if (const char *v = getenv("BIOEM_B200_CACHED_PRODUCT"))
     zmode = h->ctf_is_real && h->d_kreal && atoi(v) != 0;
+  if (h->generic)
+  {
+    zmode = false;
+    RC(dev_realloc(h, h->d_values, (size_t) OB * h->C * h->M * h->nw * h->nw));
+  }
   if (zmode)
   {
     int dev_sms = 0, ctas = 0;
@@ -1047,6 +1128,32 @@ static void fill_lik_params(bioem_b200_context *h, LikParams &lp, int o0, int OB
   lp.ex2coef = (float) (lp.acoef_d * 1.4426950408889634074);
 }
 
+// stages 3-5 of one batch on the direct-DFT path: correlation windows into d_values, then calc_logpro + calProb per
+// particle in (orientation, CTF) order straight into the running state (the record carries its displacement: there
+// is no separate exact arg-max pass on this path)
+static int gen_corr_launch(bioem_b200_context *h, const float4 *refs, int M, int nspec, float *values)
+{
+  const int N = h->N;
+  const size_t smem = gen_corr_smem(N, h->nw);
+  CU(cudaFuncSetAttribute(gen_corr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  gen_corr_kernel<<<dim3(M, nspec), 256, smem, h->stream>>>(reinterpret_cast<const float2 *>(h->d_conv),
+                                                            reinterpret_cast<const float2 *>(refs), h->d_tw_inv, h->d_wl, N,
+                                                            2 * h->map4, h->nw, M, 1.0f / (float) (N * N), values);
+  CU(cudaGetLastError());
+  return BIOEM_B200_OK;
+}
+static int run_generic_batch(bioem_b200_context *h, int o0, int OBcur)
+{
+  RC(gen_corr_launch(h, h->d_refs, h->M, OBcur * h->C, h->d_values));
+  gen_fold_kernel<<<h->M, 128, 0, h->stream>>>(h->d_values, h->d_cpar, h->d_sumRef, h->d_sumsqRef, OBcur, h->C, h->M, h->nw, o0,
+                                               h->cfg.Ntotpi, (double) (3.f - h->cfg.Ntotpi) * 0.5, h->d_state,
+                                               h->cfg.writeAngles ? h->d_angtab : nullptr);
+  CU(cudaGetLastError());
+  h->launches += 2;
+  h->likelihoods += (long long) OBcur * h->C * h->M;
+  return BIOEM_B200_OK;
+}
+
 int bioem_b200_run(bioem_b200_handle h, int oBegin, int oEnd)
 {
   if (!h)
@@ -1071,6 +1178,13 @@ int bioem_b200_run(bioem_b200_handle h, int oBegin, int oEnd)
     rc = run_front(h, o0, OBcur);
     if (rc)
       return rc;
+    if (h->generic)
+    {
+      rc = run_generic_batch(h, o0, OBcur);
+      if (rc)
+        return rc;
+      continue;
+    }
     LikParams lp;
     fill_lik_params(h, lp, o0, OBcur);
     const int NG = (OBcur + h->OG - 1) / h->OG;
@@ -1111,7 +1225,7 @@ int bioem_b200_run(bioem_b200_handle h, int oBegin, int oEnd)
 // per particle on top of nOrient x nCtf: cost below 0.1 % of a run.
 static int refine_argmax(bioem_b200_context *h)
 {
-  if (h->argmax_exact)
+  if (h->argmax_exact || h->generic) // (direct-DFT path: every record already carries its exact displacement)
     return BIOEM_B200_OK;
   // (the fused kernel does not track displacements at all, so this pass is what fills them in)
   if (h->A <= 0 || h->O <= 0 || h->C <= 0 || h->M <= 0 || (int) h->h_angles.size() != h->O)
@@ -1721,6 +1835,17 @@ int bioem_b200_debug_correlation(bioem_b200_handle h, int o, int c, int m, float
   if (rc)
     return rc;
   const size_t nv = (size_t) h->nw * h->nw;
+  if (h->generic)
+  {
+    DevTmp t_val(h);
+    RC(t_val.alloc(sizeof(float) * nv * h->C));
+    RC(gen_corr_launch(h, h->d_refs + (size_t) m * h->map4, 1, h->C, t_val.as<float>()));
+    CU(cudaMemcpyAsync(values, t_val.as<float>() + (size_t) c * nv, sizeof(float) * nv, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (nvalues)
+      *nvalues = (int) nv;
+    return BIOEM_B200_OK;
+  }
   DevTmp t_dbg(h), t_part(h);
   RC(t_dbg.alloc(sizeof(float) * nv * h->C));
   RC(t_part.alloc(sizeof(Running)));

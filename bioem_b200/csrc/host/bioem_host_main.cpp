@@ -230,7 +230,9 @@ int main(int argc, char **argv)
   }
 
   if (!bioem_b200_supported_size(par.N))
-    fail("NUMBER_PIXELS %d is not an image edge the B200 kernels are instantiated for", par.N);
+    printf("NUMBER_PIXELS %d has no fused FFT kernel (even edges 16..512 with prime factors 2/3/5/7 have): running on "
+           "the direct-DFT path, same results, many times slower\n",
+           par.N);
   int ndev = bioem_b200_device_count();
   if (ndev == 0)
     fail("no CUDA device: bioEM_b200 has no CPU path");

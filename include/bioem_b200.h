@@ -40,7 +40,7 @@ typedef struct bioem_b200_context *bioem_b200_handle;
  * reference bioem.cpp:1627,1715-1750). */
 typedef struct bioem_b200_config
 {
-  int NumberPixels;      /* N, even; see bioem_b200_supported_size() */
+  int NumberPixels;      /* N; see bioem_b200_supported_size() for the edges with a fused FFT kernel */
   int maxDisplaceCenter; /* DISPLACE_CENTER first value  */
   int GridSpaceCenter;   /* DISPLACE_CENTER second value (need not divide the first: the window is the one
                             the reference's Algo 1 enumerates, bioem_algorithm.h:156-197) */
@@ -94,7 +94,10 @@ const char *bioem_b200_last_error(void);
 int bioem_b200_version(void);
 /* number of visible CUDA devices (0 when there is none; never an error) */
 int bioem_b200_device_count(void);
-/* 1 if N is an image edge the kernels are instantiated for */
+/* 1 if N is an image edge the fused FFT kernel is instantiated for (every even edge 16..512 with prime factors 2/3/5/7
+ * except 490).  Any other edge from 2 to 4096 -- odd ones included, which the reference accepts (param.cpp:140-152,
+ * Parseval weights bioem.cpp:1893-1918) -- is accepted by create() as well and runs on the direct-DFT path: same
+ * stages and results, plain O(N^2)-per-line transforms, many times slower. */
 int bioem_b200_supported_size(int NumberPixels);
 
 /* replaces bioem_cuda_create() + deviceInit() (reference bioem_cuda.cu:818-911) */
