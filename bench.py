@@ -313,6 +313,7 @@ def run_ours(args):
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e_val = likelihoods_step * e2e_steps / float(te.item())
 
+    kmode = eng.cached_product()
     if rank == 0:
         hbm_peak, peak_src = _peaks()
         F = N * (N // 2 + 1)
@@ -361,7 +362,12 @@ def run_ours(args):
                                    + (f" [slice of the named {o_full} x {m_full} shape]" if sliced else ""),
                        "likelihoods_per_step": likelihoods_step,
                        "parallelism": f"orientation-sharded x{world}, merge = one ncclAllGather inside the library" if world > 1 else "single GPU",
-                       "l2": f"inputs larger than L2 (particle spectra {M * 8 * F / 1e6:.0f} MB re-streamed per orientation group + up to 1.07 GB of conv spectra per launch)"},
+                       # which operands the fused kernel streams (bioem_b200_cached_product): real CTF kernels -> the
+                       # product projection x conj(particle), cached per resident CTA, and the real CTF tables
+                       "kernel_mode": {1: "cached product (real CTF kernels)", 0: "complex conv spectra"}.get(kmode, "undecided"),
+                       "l2": f"inputs larger than L2 (particle spectra {M * 8 * F / 1e6:.0f} MB re-streamed per orientation group"
+                             + (" + one scratch map per resident CTA)" if kmode == 1 else
+                                " + up to 1.07 GB of conv spectra per launch)")},
             "clocks": clocks,
             "e2e": {"value": round(e2e_val, 1) if e2e_val else None, "unit": "likelihoods/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "steps": e2e_steps},

@@ -1178,16 +1178,6 @@ int bioem_b200_run(bioem_b200_handle h, int oBegin, int oEnd)
     rc = run_front(h, o0, OBcur);
     if (rc)
       return rc;
-    if (h->generic)
-    {
-      rc = run_generic_batch(h, o0, OBcur);
-      if (rc)
-        return rc;
-      continue;
-    }
-    LikParams lp;
-    fill_lik_params(h, lp, o0, OBcur);
-    const int NG = (OBcur + h->OG - 1) / h->OG;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->time_kernels)
     {
@@ -1203,16 +1193,28 @@ int bioem_b200_run(bioem_b200_handle h, int oBegin, int oEnd)
       }
       CU(cudaEventRecord(e0, h->stream));
     }
-    CU(do_lik(h->N, lp, h->M * NG, h->cfg.maxDisplaceCenter, h->stream));
+    LikParams lp;
+    fill_lik_params(h, lp, o0, OBcur);
+    const int NG = (OBcur + h->OG - 1) / h->OG;
+    if (h->generic)
+    {
+      rc = run_generic_batch(h, o0, OBcur);
+      if (rc)
+        return rc;
+    }
+    else
+      CU(do_lik(h->N, lp, h->M * NG, h->cfg.maxDisplaceCenter, h->stream));
     if (h->time_kernels)
     {
       CU(cudaEventRecord(e1, h->stream));
       h->lik_events.emplace_back(e0, e1);
     }
+    h->lik_launches += 1;
+    if (h->generic)
+      continue;
     merge_partials_kernel<<<(h->M + 127) / 128, 128, 0, h->stream>>>(h->d_partials, NG, h->M, h->d_state);
     CU(cudaGetLastError());
     h->launches += 2;
-    h->lik_launches += 1;
     h->likelihoods += (long long) OBcur * h->C * h->M;
     h->argmax_exact = false;
   }

@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(256) gen_conv_kernel(const float2 *__restrict_
 // Correlation window of one (conv spectrum, particle) item: values[item][wx*nw + wy] = lCC[x][y] / N^2 for the
 // window displacements x = wl[wx], y = wl[wy] (doRefMapFFT's enumeration, bioem_algorithm.h:156-197), where lCC is
 // the c2r inverse transform of conv * conj(particle).  Two partial DFTs through shared memory:
-//   T[wx][k1] = sum_k0 Z[k0][k1] exp(+2 pi i k0 x / N)                       (thread = k1, XB window rows at a time)
+//   T[wx][k1] = sum_k0 Z[k0][k1] exp(+2 pi i k0 x / N)                       (thread = k1 x a block of XB window rows)
 //   lCC[x][y] = sum_k1 w(k1) Re(T[wx][k1] exp(+2 pi i k1 y / N)),  w = 1 for the self-conjugate columns, else 2
 // (a c2r transform sees exactly that much of the half-spectrum: quirk Q1 needs no special case here).
 // Grid: x = particle, y = conv spectrum of the batch.
@@ -165,9 +165,12 @@ __global__ void __launch_bounds__(256) gen_corr_kernel(const float2 *__restrict_
   __syncthreads();
   const float2 *V = convs + (size_t) oc * S;
   const float2 *R = refs + (size_t) m * S;
-  for (int k1 = tid; k1 < NC; k1 += blockDim.x)
+  // work item = (block of XB window rows, column k1): consecutive threads take consecutive columns of the same block
+  // (coalesced operand loads, broadcast twiddle reads)
+  const int nxb = (nw + GEN_XB - 1) / GEN_XB;
+  for (int item = tid; item < nxb * NC; item += blockDim.x)
   {
-    for (int w0 = 0; w0 < nw; w0 += GEN_XB)
+    const int k1 = item % NC, w0 = (item / NC) * GEN_XB;
     {
       float2 acc[GEN_XB];
       int idx[GEN_XB], step[GEN_XB];
