@@ -118,7 +118,8 @@ def lib():
     L.bioem_b200_set_kernel_timing.argtypes = [vp, C.c_int]
     L.bioem_b200_out_of_frame.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_longlong)]
     L.bioem_b200_exact_argmax_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
-    L.bioem_b200_cached_product.argtypes = [vp]
+    if hasattr(L, "bioem_b200_cached_product"):  # (absent from libraries built before the cached-product mode: A/B runs)
+        L.bioem_b200_cached_product.argtypes = [vp]
     L.bioem_b200_stream.argtypes = [vp]
     L.bioem_b200_stream.restype = vp
     L.bioem_b200_device_angles.argtypes = [vp]
