@@ -9,6 +9,7 @@
   here, afterwards:                python tools/profile_pass.py post <label> <round, e.g. r01>
       writes profiles/<round>_bench_<label>.json, <round>_launches_<label>_summary.csv,
       <round>_likelihood_kernel_<label>_ncu.txt and refreshes profiles/ncu_traffic.json
+  any other capture:               python tools/profile_pass.py summarise <rep> <likelihoods per launch> <plain.log> <out.txt> <title> <command>
 """
 import csv
 import io
@@ -40,6 +41,37 @@ def gpu(label):
         sys.exit("prof_lik.py failed without a profiler: not profiling")
     sh("ncu --set full --clock-control none --import-source on -k regex:likelihood_kernel -s 1 -c 1 "
        f"-o gpurun_out/prof_{label} -f python tools/prof_lik.py cfg2 150 > gpurun_out/prof_{label}_ncu.log 2>&1")
+
+
+UNITS = ["SM_A.TriageCompute.l1tex__data_pipe_lsu_wavefronts.avg", "SM_A.TriageCompute.l1tex__data_pipe_lsu_wavefronts_mem_lgds.avg",
+         "SM_A.TriageCompute.l1tex__data_pipe_lsu_wavefronts_mem_shared.avg",
+         "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+         "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "sm__cycles_active.avg",
+         "sm__inst_issued.avg.pct_of_peak_sustained_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+         "smsp__warps_eligible.avg.per_cycle_active", "dram__bytes_read.sum", "dram__bytes_write.sum"]
+
+
+def summarise(rep, nlik, plain, out, title, command):
+    """key counters, stall table, opcode mix, unit utilisation and hottest SASS lines of one capture -> a text file"""
+    summ = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), rep, str(nlik)],
+                          capture_output=True, text=True).stdout
+    hot = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_hot.py"), rep], capture_output=True, text=True).stdout
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    d = dict(zip(rows[0], rows[2]))
+    with open(out, "w") as f:
+        f.write(f"# {title} -- ncu --set full --clock-control none --import-source on\n")
+        f.write(f"# command: {command}   (plain run of the same command first: next line)\n")
+        f.write(open(plain).read())
+        f.write(f"# one launch = {int(nlik):,} likelihoods\n")
+        f.write(summ + "\n# unit utilisation:\n")
+        for k in UNITS:
+            f.write(f"{k} = {d.get(k)}\n")
+        sectors = float(d.get("lts__t_sectors_srcunit_tex_op_read.sum", "nan"))
+        f.write(f"L2 -> SM bytes per likelihood = {32.0 * sectors / float(nlik):.0f}\n")
+        f.write("\n# hottest SASS lines (share of warp-stall samples, dominant stall reasons):\n")
+        f.write("\n".join(hot.split("\n")[:14]) + "\n")
+    print("written", out)
 
 
 def post(label, rnd):
@@ -106,5 +138,7 @@ if __name__ == "__main__":
         gpu(sys.argv[2])
     elif len(sys.argv) >= 4 and sys.argv[1] == "post":
         post(sys.argv[2], sys.argv[3])
+    elif len(sys.argv) >= 8 and sys.argv[1] == "summarise":
+        summarise(*sys.argv[2:8])
     else:
         sys.exit(__doc__)
